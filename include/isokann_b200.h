@@ -1,0 +1,194 @@
+/* libisokann_b200.so -- C ABI of the B200-native ISOKANN per-iteration hot path.
+ *
+ * Drop-in boundary for axsk/ISOKANN.jl.  The reference has no FFI: its plugin API is
+ * Julia multiple dispatch.  Each entry point below names the reference interface it
+ * replaces (file:line under the reference checkout).  The Julia-side `ccall` shim is
+ * julia/ISOKANNB200.jl; in this repo the same ABI is driven from
+ * Python ctypes (isokann.jl_b200/lib.py).
+ *
+ * Conventions
+ *  - every function returns an int32 status (ISOKANN_OK == 0); no C++ exception crosses
+ *    the boundary; isokann_last_error(ctx) gives the message of the last failure.
+ *  - pointers are HOST pointers to caller-owned, contiguous, COLUMN-MAJOR (Julia) arrays
+ *    unless the parameter name starts with `dev_`; the library copies in/out and owns all
+ *    device memory behind the opaque handle.
+ *      xs[D,N]   : N records of D floats          ys[D,K,N] : for each n, K records of D floats
+ *      chi[d,N]  : N records of d floats          W[out,in] : Flux.Dense weight, column-major
+ *  - flat parameter order = Functors traversal of the Flux.Chain:
+ *      [LayerNorm.scale(F), LayerNorm.bias(F),]  W1(out x in col-major), b1, W2, b2, ...
+ *  - index arguments (perm, atom indices, pairs) are 1-based, as Julia produces them.
+ *  - single caller: one host thread drives one context; the library is not re-entrant.
+ *  - there is NO CPU fallback: without a CUDA device isokann_create fails with
+ *    ISOKANN_ERR_CUDA.
+ */
+#ifndef ISOKANN_B200_H
+#define ISOKANN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISOKANN_ABI_VERSION 1
+#define ISOKANN_MAX_LAYERS 8
+
+/* status codes; 1..4 are the reference's DomainErrors and must be re-thrown as such */
+enum {
+  ISOKANN_OK = 0,
+  ISOKANN_DOMAIN_CONSTANT_CHI = 1,     /* src/isotarget.jl:39  "chi function is constant"            */
+  ISOKANN_DOMAIN_NONFINITE_LOSS = 2,   /* src/iso.jl:186-189   "model collapsed under training"      */
+  ISOKANN_DOMAIN_SINGULAR_SIMPLEX = 3, /* src/isotarget.jl:94-97 "simplex transformation"            */
+  ISOKANN_DOMAIN_PINV = 4,             /* src/isotarget.jl:159-163 "pseudoinverse"                   */
+  ISOKANN_BAD_ARGUMENT = 5,            /* e.g. shiftscale with d>1 (src/isotarget.jl:37)             */
+  ISOKANN_ERR_CUDA = 10,
+  ISOKANN_ERR_NCCL = 11,
+  ISOKANN_ERR_STATE = 12               /* call order (no data / no target yet)                       */
+};
+
+enum { ISOKANN_ACT_IDENTITY = 0, ISOKANN_ACT_SIGMOID = 1, ISOKANN_ACT_TANH = 2, ISOKANN_ACT_RELU = 3 };
+enum { ISOKANN_OPT_NESTEROV = 0, ISOKANN_OPT_ADAM = 1 };
+/* featurizer functors, src/utils/features.jl:18-35 */
+enum {
+  ISOKANN_FEAT_IDENTITY = 0, /* FeaturesCoords / `identity` (ExternalSimulation, Langevin) */
+  ISOKANN_FEAT_ALLPAIRS = 1, /* FeaturesAll   -> flatpairdists(x)        src/utils/pairdists.jl:6-24  */
+  ISOKANN_FEAT_ATOMS = 2,    /* FeaturesAtoms -> flatpairdists(x, inds)  src/utils/pairdists.jl:13-16 */
+  ISOKANN_FEAT_PAIRS = 3     /* FeaturesPairs -> pdists(x, pairs)        src/utils/pairdists.jl:109-127 */
+};
+/* isotarget transforms, src/isotarget.jl:32,74,145 */
+enum { ISOKANN_TARGET_SHIFTSCALE = 0, ISOKANN_TARGET_ISA = 1, ISOKANN_TARGET_PINV = 2 };
+/* GEMM engine for the Dense layers */
+enum {
+  ISOKANN_GEMM_AUTO = 0,   /* tcgen05 for wide layers (in,out >= 256), FP32 CUDA cores otherwise */
+  ISOKANN_GEMM_FP32 = 1,   /* FP32 FFMA everywhere                                               */
+  ISOKANN_GEMM_TC = 2      /* tcgen05 3xBF16 split (fp32-accurate) wherever shapes allow          */
+};
+
+typedef struct isokann_ctx isokann_ctx;
+
+/* Model / optimiser / featurizer description: replaces pairnet/densenet/smallnet
+ * (src/models.jl:65-69,87-92,102-108), AdamRegularized/NesterovRegularized (src/models.jl:12,20)
+ * + Flux.setup (src/iso.jl:27) and the featurizer functor (src/utils/features.jl:18-35). */
+typedef struct {
+  int32_t n_layers;                        /* number of Dense layers L                          */
+  int32_t widths[ISOKANN_MAX_LAYERS + 1];  /* F, h1, ..., d                                      */
+  int32_t layernorm;                       /* 1: Flux.LayerNorm(F) in front (src/models.jl:90)   */
+  float ln_eps;                            /* Flux default 1f-5: (x-mu)/sqrt(var+eps^2)          */
+  int32_t activation;                      /* hidden layers (Flux.sigmoid)                       */
+  int32_t last_activation;                 /* last layer (identity)                              */
+  int32_t optimiser;                       /* ISOKANN_OPT_*                                      */
+  float eta, lambda, beta1, beta2, eps, rho;
+  int32_t featurizer;                      /* ISOKANN_FEAT_*                                     */
+  int32_t n_atoms;                         /* A; a coordinate record has D = 3A floats           */
+  int32_t n_index;                         /* ATOMS: #atoms; PAIRS: #pairs                       */
+  const int32_t *index;                    /* ATOMS: 1-based atom ids; PAIRS: (a1,b1,a2,b2,...)  */
+  int32_t device;                          /* CUDA device ordinal                                */
+  int32_t gemm_mode;                       /* ISOKANN_GEMM_*                                     */
+  int64_t chunk;                           /* samples per forward chunk (0 = library default)    */
+} isokann_config;
+
+/* options of TransformISA (src/isotarget.jl:74-77) and TransformPseudoInv (:145-150) */
+typedef struct {
+  int32_t permute;    /* both, default 1 */
+  int32_t whitening;  /* ISA, default 0 */
+  int32_t normalize;  /* PseudoInv, default 1 */
+  int32_t direct;     /* PseudoInv, default 1 */
+  int32_t eigenvecs;  /* PseudoInv, default 1 */
+} isokann_target_opts;
+
+typedef struct {
+  int64_t kernel_launches;   /* kernels launched by this library since create / reset         */
+  int64_t nccl_calls;
+  double ms_featurize;       /* accumulated CUDA-event times per kernel class (only while      */
+  double ms_gemm;            /* timing is enabled with isokann_enable_timing)                  */
+  double ms_reduce;
+  double ms_train_elementwise;
+  double ms_optimiser;
+  double ms_koopman_total;   /* whole expectation(model, ys) pass                              */
+  double ms_target_total;
+  double ms_train_total;
+  int64_t n_gemm_launches;
+  int64_t n_featurize_launches;
+  double gemm_flops;         /* algorithmic 2*M*N*K of the GEMMs timed in ms_gemm             */
+  double featurize_bytes;    /* algorithmic 4*(D+F)*M of the launches timed in ms_featurize   */
+} isokann_stats;
+
+int32_t isokann_abi_version(void);
+
+/* Iso(data; model, opt) -> handle (src/iso.jl:17-43).  Parameters are zero until uploaded. */
+int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out);
+int32_t isokann_destroy(isokann_ctx *ctx);
+const char *isokann_last_error(const isokann_ctx *ctx);
+
+int64_t isokann_num_params(const isokann_ctx *ctx);
+int32_t isokann_feature_dim(const isokann_ctx *ctx);  /* F implied by the featurizer          */
+int32_t isokann_coord_dim(const isokann_ctx *ctx);    /* D expected in coordinate records      */
+
+/* Multi-GPU: one process per GPU.  Rank 0 obtains the 128-byte NCCL id, the host broadcasts
+ * it (torch.distributed / MPI / Distributed.jl) and every rank joins.  Not in the reference
+ * (no multi-GPU there); numbers must equal the 1-GPU run up to fp32 summation order. */
+int32_t isokann_comm_get_unique_id(void *id128);
+int32_t isokann_comm_init(isokann_ctx *ctx, int32_t world, int32_t rank, const void *id128);
+
+/* SimulationData(xs, ys; featurizer) (src/simulation.jl:100-114): uploads coordinates; the
+ * Float32 feature cast of :112 happens on device.  ys may be NULL (inference only). */
+int32_t isokann_set_data(isokann_ctx *ctx, const float *xs, const float *ys, int64_t D, int64_t K, int64_t N);
+int32_t isokann_set_data_f64(isokann_ctx *ctx, const double *xs, const double *ys, int64_t D, int64_t K, int64_t N);
+/* Sharded form: xs is the full D x N on every rank, ys_local holds the start points
+ * [n_offset, n_offset+n_local) of this rank only. */
+int32_t isokann_set_data_sharded(isokann_ctx *ctx, const float *xs, const float *ys_local, int64_t D, int64_t K,
+                                 int64_t N, int64_t n_offset, int64_t n_local);
+/* Same with buffers already resident on this context's device (no copy of ys: it is adopted by
+ * reference and must stay alive until the next set_data / destroy). */
+int32_t isokann_set_data_dev(isokann_ctx *ctx, const float *dev_xs, const float *dev_ys_local, int64_t D, int64_t K,
+                             int64_t N, int64_t n_offset, int64_t n_local);
+/* WeightedSamples (Girsanov) weights for the resident ys, K x n_local (src/data.jl:187-215);
+ * NULL clears them. */
+int32_t isokann_set_koopman_weights(isokann_ctx *ctx, const float *weights_local);
+
+/* gpu(iso)/cpu(iso), save/load (src/iso.jl:256-257,405-420): parameter and optimiser-state sync */
+int32_t isokann_upload_params(isokann_ctx *ctx, const float *flat, int64_t P);
+int32_t isokann_download_params(isokann_ctx *ctx, float *flat, int64_t P);
+/* Adam: m, v (P each) + beta_t[2]; Nesterov: m = velocity, v and beta_t may be NULL */
+int32_t isokann_upload_opt_state(isokann_ctx *ctx, const float *m, const float *v, const float *beta_t, int64_t P);
+int32_t isokann_download_opt_state(isokann_ctx *ctx, float *m, float *v, float *beta_t, int64_t P);
+
+/* featurizer(coords) (src/simulation.jl:112,121-124; src/utils/features.jl:22-35) -> F x M */
+int32_t isokann_featurize(isokann_ctx *ctx, const float *coords, int64_t D, int64_t M, float *features_out);
+/* model(x) (src/iso.jl:203 chis, :211 chicoords; src/isotarget.jl:18,101,154): rows == D
+ * (coordinates, is_features == 0) or rows == F (features, is_features == 1) -> d x M */
+int32_t isokann_forward(isokann_ctx *ctx, const float *in, int64_t rows, int64_t M, int32_t is_features,
+                        float *chi_out);
+/* chis(iso) on the resident xs -> d x N */
+int32_t isokann_chis(isokann_ctx *ctx, float *chi_out);
+/* expectation(model, propfeatures(data)) (src/isotarget.jl:18,20) on the resident ys -> d x N */
+int32_t isokann_koopman(isokann_ctx *ctx, float *kchi_out);
+/* isotarget(target, model, xs, ys) (src/isotarget.jl:12,34,100-107,152-179); the target stays
+ * resident for train_epoch; target_out (d x N) may be NULL */
+int32_t isokann_target(isokann_ctx *ctx, int32_t transform, const isokann_target_opts *opts, float *target_out);
+/* user-defined isotarget methods: upload a d x N target computed on the host */
+int32_t isokann_set_target(isokann_ctx *ctx, const float *target, int64_t d, int64_t N);
+/* train_batch!(model, xs, target, opt, minibatch; shuffle, partial) (src/iso.jl:179-194).  perm
+ * is the 1-based randperm(N) the DataLoader would draw; returns sum(l)/N in *loss_out */
+int32_t isokann_train_epoch(isokann_ctx *ctx, const int64_t *perm, int64_t minibatch, int32_t partial,
+                            double *loss_out);
+/* run!(iso, n, epochs) (src/iso.jl:72-94) without host round trips: perms holds
+ * n_iter*epochs permutations of length N; losses_out receives n_iter*epochs values */
+int32_t isokann_iterate(isokann_ctx *ctx, int32_t transform, const isokann_target_opts *opts, int64_t n_iter,
+                        int64_t epochs, int64_t minibatch, const int64_t *perms, double *losses_out);
+
+int32_t isokann_enable_timing(isokann_ctx *ctx, int32_t on);
+int32_t isokann_get_stats(isokann_ctx *ctx, isokann_stats *out);
+int32_t isokann_reset_stats(isokann_ctx *ctx);
+int32_t isokann_synchronize(isokann_ctx *ctx);
+/* the CUDA stream all kernels of this context are launched on (for external event timing) */
+void *isokann_stream(isokann_ctx *ctx);
+
+/* host-side small dense algebra used by the N-D targets, exposed for CPU tests:
+ * real Schur vectors of a d x d float matrix (column-major in/out), LAPACK sgees conventions */
+int32_t isokann_host_schur(const float *a_colmajor, int32_t d, float *z_colmajor, float *t_colmajor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISOKANN_B200_H */

@@ -1,0 +1,1092 @@
+// C ABI of libisokann_b200 (include/isokann_b200.h): host orchestration of the ISOKANN
+// iteration  featurize -> chi forward over K*N -> K-mean -> isotarget -> minibatched
+// fwd/bwd -> optimiser  (reference src/iso.jl:72-94,179-194; src/isotarget.jl:10-42,74-179).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+using namespace ik;
+
+struct isokann_ctx : public ik::Ctx {};
+
+// ------------------------------------------------------------------------------------------
+// event timers
+// ------------------------------------------------------------------------------------------
+namespace ik {
+
+void EventTimer::begin(int cls, cudaStream_t s) {
+  if (!enabled) return;
+  if (used == pool.size()) {
+    Pair p;
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+    pool.push_back(p);
+  }
+  pool[used].cls = cls;
+  cudaEventRecord(pool[used].a, s);
+  open.push_back(used);
+  used++;
+}
+
+void EventTimer::end(cudaStream_t s) {
+  if (!enabled || open.empty()) return;
+  cudaEventRecord(pool[open.back()].b, s);
+  open.pop_back();
+}
+
+void EventTimer::flush(cudaStream_t s) {
+  if (!enabled || used == 0) return;
+  cudaStreamSynchronize(s);
+  for (size_t i = 0; i < used; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, pool[i].a, pool[i].b) == cudaSuccess) ms[pool[i].cls] += t;
+  }
+  used = 0;
+  open.clear();
+}
+
+void EventTimer::destroy() {
+  for (auto &p : pool) {
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  pool.clear();
+  used = 0;
+}
+
+}  // namespace ik
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_create_err;
+
+template <typename Fn>
+int32_t guarded(isokann_ctx *ctx, Fn &&fn) {
+  if (!ctx) return ISOKANN_BAD_ARGUMENT;
+  try {
+    cudaSetDevice(ctx->dev);
+    fn();
+    return ISOKANN_OK;
+  } catch (const ik::Error &e) {
+    ctx->err = e.msg;
+    // leave the device in a clean state for the next call
+    if (e.code == ISOKANN_ERR_CUDA) cudaGetLastError();
+    return e.code;
+  } catch (const std::exception &e) {
+    ctx->err = e.what();
+    return ISOKANN_ERR_STATE;
+  }
+}
+
+// contiguous split of [0, n) over `world` ranks
+void split_range(int64_t n, int world, int rank, int64_t *off, int64_t *len) {
+  const int64_t base = n / world, rem = n % world;
+  *off = rank * base + std::min<int64_t>(rank, rem);
+  *len = base + (rank < rem ? 1 : 0);
+}
+
+void sync_stream(Ctx &c) { IK_CUDA(cudaStreamSynchronize(c.stream)); }
+
+void ensure_pinned(Ctx &c, size_t bytes) {
+  if (bytes <= c.pinned_bytes) return;
+  if (c.pinned) cudaFreeHost(c.pinned);
+  c.pinned = nullptr;
+  c.pinned_bytes = 0;
+  IK_CUDA(cudaMallocHost(&c.pinned, bytes));
+  c.pinned_bytes = bytes;
+}
+
+// device -> pinned host, synchronous
+template <typename T>
+T *read_back(Ctx &c, const T *dev, size_t count) {
+  ensure_pinned(c, count * sizeof(T));
+  IK_CUDA(cudaMemcpyAsync(c.pinned, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c.stream));
+  sync_stream(c);
+  return reinterpret_cast<T *>(c.pinned);
+}
+
+int check_flags(Ctx &c) {
+  int *f = read_back(c, c.flags.p, 1);
+  const int v = *f;
+  if (v) IK_CUDA(cudaMemsetAsync(c.flags.p, 0, sizeof(int), c.stream));
+  return v;
+}
+
+void ensure_act(Ctx &c, int64_t rows) {
+  if (rows <= c.act_rows) return;
+  for (int l = 0; l <= c.L; ++l) c.act[l].ensure((size_t)rows * c.cfg.widths[l]);
+  c.act_rows = rows;
+}
+
+const float *layer_segment(Ctx &c, int l) {
+  if (l == 0 && c.ln) return c.folded1.p;
+  return c.params.p + c.off_w[l];
+}
+
+void ensure_folded(Ctx &c) {
+  if (!c.ln || c.folded_valid) return;
+  launch_fold_ln(c, c.params.p + c.off_gamma, c.params.p + c.off_beta, c.params.p + c.off_w[0],
+                 c.params.p + c.off_b[0], c.F, c.cfg.widths[1], c.folded1.p);
+  c.folded_valid = true;
+}
+
+// featurize (+ parameter-free LayerNorm) M records and run all Dense layers; results stay in
+// c.act[0..L] (row-major M x width).  `in` holds coordinate records (in_is_coords) or features.
+void forward_rows(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords) {
+  if (M <= 0) return;
+  ensure_act(c, M);
+  ensure_folded(c);
+  const bool pairs = in_is_coords && c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
+  launch_featurize(c, in, gather, goff, M, pairs, c.ln, c.act[0].p, c.F);
+  for (int l = 0; l < c.L; ++l) {
+    const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
+    GemmP p{};
+    p.A = c.act[l].p; p.lda = fin;
+    p.B = layer_segment(c, l); p.ldb = fout;
+    p.C = c.act[l + 1].p; p.ldc = fout;
+    p.M = (int)M; p.N = fout; p.K = fin + 1;
+    p.ones_k = fin; p.ones_i = -1;
+    p.act = (l < c.L - 1) ? c.cfg.activation : c.cfg.last_activation;
+    p.epi = EPI_ACT;
+    launch_gemm(c, p, true, true, 1);
+  }
+}
+
+int64_t chunk_rows(const Ctx &c, int64_t multiple) {
+  int64_t ch = c.cfg.chunk > 0 ? c.cfg.chunk : 65536;
+  // keep the widest activation buffer below ~1 GiB
+  const int64_t cap = std::max<int64_t>(1024, (int64_t)(1ull << 28) / std::max(1, c.maxw));
+  ch = std::min(ch, cap);
+  if (multiple > 1) ch = std::max<int64_t>(multiple, ch / multiple * multiple);
+  return ch;
+}
+
+// chi for M device-resident records -> dev_out (M x d)
+void forward_to(Ctx &c, const float *dev_in, int64_t M, bool in_is_coords, float *dev_out) {
+  const int64_t rowlen = in_is_coords ? c.D : c.F;
+  const int64_t ch = chunk_rows(c, 1);
+  for (int64_t m0 = 0; m0 < M; m0 += ch) {
+    const int64_t m = std::min(ch, M - m0);
+    forward_rows(c, dev_in + m0 * rowlen, nullptr, 0, m, in_is_coords);
+    IK_CUDA(cudaMemcpyAsync(dev_out + m0 * c.d, c.act[c.L].p, (size_t)m * c.d * sizeof(float),
+                            cudaMemcpyDeviceToDevice, c.stream));
+  }
+}
+
+void allgather_rows(Ctx &c, const float *local, int64_t n_local, float *full) {
+  // shards follow split_range(N); pad every shard to nmax rows for the fixed-size collective
+  const int64_t nmax = (c.N + c.world - 1) / c.world;
+  c.gather_pad.ensure((size_t)(c.world + 1) * nmax * c.d);
+  float *send = c.gather_pad.p + (size_t)c.world * nmax * c.d;
+  IK_CUDA(cudaMemsetAsync(send, 0, (size_t)nmax * c.d * sizeof(float), c.stream));
+  IK_CUDA(cudaMemcpyAsync(send, local, (size_t)n_local * c.d * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  std::string err;
+  int rc = nccl_allgather_f32(c.nccl, c.comm, send, c.gather_pad.p, (size_t)nmax * c.d, c.stream, err);
+  IK_REQUIRE(rc == ISOKANN_OK, ISOKANN_ERR_NCCL, err);
+  c.stats.nccl_calls++;
+  launch_compact_gather(c, c.gather_pad.p, c.world, nmax, c.N, c.d, full);
+}
+
+// chis(iso): model(features(xs)) on the resident start points -> c.chi_x (N x d)
+void compute_chis(Ctx &c) {
+  IK_REQUIRE(c.xs != nullptr, ISOKANN_ERR_STATE, "no data: call isokann_set_data first");
+  c.chi_x.ensure((size_t)c.N * c.d);
+  if (c.world == 1) {
+    forward_to(c, c.xs, c.N, true, c.chi_x.p);
+  } else {
+    c.kchi_loc.ensure((size_t)std::max<int64_t>(1, c.n_loc) * c.d);
+    forward_to(c, c.xs + c.n_off * c.D, c.n_loc, true, c.kchi_loc.p);
+    allgather_rows(c, c.kchi_loc.p, c.n_loc, c.chi_x.p);
+  }
+}
+
+// expectation(model, ys) -> c.kchi (N x d)
+void compute_koopman(Ctx &c) {
+  IK_REQUIRE(c.ys != nullptr, ISOKANN_ERR_STATE, "no Koopman samples: call isokann_set_data with ys");
+  c.timer.begin(KC_PHASE_KOOPMAN, c.stream);
+  c.kchi.ensure((size_t)c.N * c.d);
+  float *dst = c.kchi.p;
+  if (c.world > 1) {
+    c.kchi_loc.ensure((size_t)std::max<int64_t>(1, c.n_loc) * c.d);
+    dst = c.kchi_loc.p;
+  }
+  const int64_t ch = chunk_rows(c, c.K);
+  const int64_t nsp = ch / c.K;
+  for (int64_t n0 = 0; n0 < c.n_loc; n0 += nsp) {
+    const int64_t ns = std::min(nsp, c.n_loc - n0);
+    forward_rows(c, c.ys + n0 * c.K * c.D, nullptr, 0, ns * c.K, true);
+    launch_kmean(c, c.act[c.L].p, c.has_weights ? c.kweights.p + n0 * c.K : nullptr, ns, (int)c.K, c.d,
+                 dst + n0 * c.d);
+  }
+  if (c.world > 1) allgather_rows(c, c.kchi_loc.p, c.n_loc, c.kchi.p);
+  c.timer.end(c.stream);
+}
+
+void set_unit_weights(Ctx &c) {
+  c.w_loss.ensure(kMaxD);
+  launch_fill(c, c.w_loss.p, kMaxD, 1.0f);
+}
+
+// first minimiser over lexicographic permutations of sum_b C[p_b][b]  (fixperm, src/isotarget.jl:120-127)
+void best_perm(const double *C, int d, int *perm_out) {
+  int p[kMaxD];
+  for (int i = 0; i < d; ++i) p[i] = i;
+  double best = INFINITY;
+  bool have = false;
+  do {
+    double s = 0.0;
+    for (int b = 0; b < d; ++b) s += C[p[b] * d + b];
+    if (!have || s < best) {
+      best = s;
+      have = true;
+      for (int i = 0; i < d; ++i) perm_out[i] = p[i];
+    }
+  } while (std::next_permutation(p, p + d));
+}
+
+void sum_partials(const double *part, int nblocks, int per_block, double *out) {
+  for (int i = 0; i < per_block; ++i) out[i] = 0.0;
+  for (int b = 0; b < nblocks; ++b)
+    for (int i = 0; i < per_block; ++i) out[i] += part[(size_t)b * per_block + i];
+}
+
+// shared tail of the N-D targets: optional L1 normalisation, optional fixperm, final write + loss weights
+void finish_nd_target(Ctx &c, Mat8 mat, bool normalize, bool permute) {
+  const int d = c.d;
+  int nb = 0;
+  c.target.ensure((size_t)c.N * d);
+  if (normalize) {  // target ./ norm.(eachrow(target), 1) .* N   (src/isotarget.jl:175)
+    launch_apply(c, 0, c.kchi.p, nullptr, c.N, d, mat, nullptr, c.red_d.p, &nb);
+    double *part = read_back(c, c.red_d.p, (size_t)nb * d);
+    double l1[kMaxD];
+    sum_partials(part, nb, d, l1);
+    for (int a = 0; a < d; ++a) {
+      const double s = (double)c.N / l1[a];
+      for (int b = 0; b < d; ++b) mat.m[a * d + b] *= s;
+    }
+  }
+  if (permute) {
+    launch_apply(c, 1, c.kchi.p, c.chi_x.p, c.N, d, mat, nullptr, c.red_d.p, &nb);
+    double *part = read_back(c, c.red_d.p, (size_t)nb * d * d);
+    double C[kMaxD * kMaxD];
+    sum_partials(part, nb, d * d, C);
+    int p[kMaxD];
+    best_perm(C, d, p);
+    Mat8 m2;
+    for (int b = 0; b < d; ++b)
+      for (int k = 0; k < d; ++k) m2.m[b * d + k] = mat.m[p[b] * d + k];
+    mat = m2;
+  }
+  launch_apply(c, 2, c.kchi.p, nullptr, c.N, d, mat, c.target.p, c.red_d.p, &nb);
+  double *part = read_back(c, c.red_d.p, (size_t)nb * d * 2);
+  double mom[2 * kMaxD];
+  sum_partials(part, nb, 2 * d, mom);
+  float w[kMaxD];
+  for (int a = 0; a < kMaxD; ++a) w[a] = 1.0f;
+  for (int a = 0; a < d; ++a) {  // w = 1 ./ std(target, dims=2), corrected  (src/iso.jl:183)
+    const double s = mom[2 * a], q = mom[2 * a + 1];
+    const double var = (q - s * s / (double)c.N) / (double)(c.N - 1);
+    w[a] = (float)(1.0 / std::sqrt(var));
+  }
+  c.w_loss.ensure(kMaxD);
+  IK_CUDA(cudaMemcpyAsync(c.w_loss.p, w, sizeof(w), cudaMemcpyHostToDevice, c.stream));
+  sync_stream(c);
+}
+
+void fetch_row(Ctx &c, const float *dev_rows, int64_t idx, int d, float *out) {
+  float *r = read_back(c, dev_rows + idx * d, (size_t)d);
+  for (int i = 0; i < d; ++i) out[i] = r[i];
+}
+
+void target_isa(Ctx &c, const isokann_target_opts &o) {
+  const int d = c.d;
+  IK_REQUIRE(d > 1, ISOKANN_BAD_ARGUMENT, "TransformISA does not work with one dimensional chi functions");
+  IK_REQUIRE(d <= kMaxD, ISOKANN_BAD_ARGUMENT, "chi dimension exceeds ISOKANN_MAX_D");
+  if (o.permute) compute_chis(c);
+  IsaReplay rp{};
+  rp.d = d;
+  rp.rounds = 0;
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) rp.pre[i * d + j] = (i == j) ? 1.0 : 0.0;
+  int nb = 0;
+  if (o.whitening) {  // C = X'X/N, W = C^(-1/2)   (src/isotarget.jl:85-88)
+    launch_gram(c, nullptr, c.kchi.p, c.N, d, c.red_d.p, &nb);
+    double *part = read_back(c, c.red_d.p, (size_t)nb * d * 2 * d);
+    double g[2 * kMaxD * kMaxD];
+    sum_partials(part, nb, d * 2 * d, g);
+    double C[kMaxD * kMaxD], ev[kMaxD], V[kMaxD * kMaxD];
+    for (int a = 0; a < d; ++a)
+      for (int b = 0; b < d; ++b) C[a * d + b] = g[a * 2 * d + d + b] / (double)c.N;
+    host_sym_eig(C, d, ev, V);
+    for (int a = 0; a < d; ++a)
+      for (int b = 0; b < d; ++b) {
+        double s = 0.0;
+        for (int k = 0; k < d; ++k) s += V[a * d + k] * (1.0 / std::sqrt(ev[k])) * V[b * d + k];
+        rp.pre[a * d + b] = s;
+      }
+    for (int i = 0; i < d * d; ++i)
+      IK_REQUIRE(std::isfinite(rp.pre[i]), ISOKANN_DOMAIN_SINGULAR_SIMPLEX,
+                 "Could not compute the simplex transformation. The subspace might be singular/collapsed");
+  }
+  long long ind[kMaxD];
+  double S[kMaxD * kMaxD];
+  for (int j = 0; j < d; ++j) {
+    launch_isa_argmax(c, c.kchi.p, c.N, rp, c.red_am.p, &nb);
+    ArgmaxPartial *part = read_back(c, c.red_am.p, (size_t)nb);
+    double best = -1.0;
+    long long bi = -1;
+    bool bestnan = false;
+    for (int b = 0; b < nb; ++b) {
+      const double v = part[b].val;
+      const long long i = part[b].idx;
+      if (i < 0) continue;
+      const bool vnan = v != v;
+      bool take;
+      if (bi < 0) take = true;
+      else if (bestnan) take = vnan && i < bi;
+      else if (vnan) take = true;
+      else take = v > best || (v == best && i < bi);
+      if (take) {
+        best = v;
+        bi = i;
+        bestnan = vnan;
+      }
+    }
+    IK_REQUIRE(bi >= 0 && !bestnan, ISOKANN_DOMAIN_SINGULAR_SIMPLEX,
+               "Could not compute the simplex transformation. The subspace might be singular/collapsed");
+    ind[j] = bi;
+    float row[kMaxD];
+    fetch_row(c, c.kchi.p, bi, d, row);
+    for (int b = 0; b < d; ++b) S[j * d + b] = (double)row[b];
+    double y[kMaxD];
+    const double nrm = isa_row_norm_host(row, rp, y);
+    if (j == 0) {
+      for (int b = 0; b < d; ++b) rp.x0[b] = y[b];
+    } else {
+      rp.r[j] = nrm;
+      for (int b = 0; b < d; ++b) rp.v[j][b] = y[b] / nrm;
+    }
+    rp.rounds = j + 1;
+  }
+  double A[kMaxD * kMaxD];
+  IK_REQUIRE(host_inverse(S, d, A), ISOKANN_DOMAIN_SINGULAR_SIMPLEX,
+             "Could not compute the simplex transformation. The subspace might be singular/collapsed");
+  Mat8 mat{};
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b < d; ++b) mat.m[a * d + b] = A[b * d + a];  // target = A' * ks
+  finish_nd_target(c, mat, false, o.permute != 0);
+}
+
+void target_pinv(Ctx &c, const isokann_target_opts &o) {
+  const int d = c.d;
+  IK_REQUIRE(d > 1, ISOKANN_BAD_ARGUMENT, "TransformPseudoInv does not work with one dimensional chi functions");
+  IK_REQUIRE(d <= kMaxD, ISOKANN_BAD_ARGUMENT, "chi dimension exceeds ISOKANN_MAX_D");
+  compute_chis(c);
+  int nb = 0;
+  launch_gram(c, c.chi_x.p, c.kchi.p, c.N, d, c.red_d.p, &nb);
+  double *part = read_back(c, c.red_d.p, (size_t)nb * d * 2 * d);
+  double g[2 * kMaxD * kMaxD];
+  sum_partials(part, nb, d * 2 * d, g);
+  double G1[kMaxD * kMaxD], G2[kMaxD * kMaxD];
+  const char *msg = "Could not compute the pseudoinverse. The subspace might be singular/collapsed";
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b < d; ++b) {
+      G1[a * d + b] = g[a * 2 * d + b];       // chi  * kchi'
+      G2[a * d + b] = g[a * 2 * d + d + b];   // kchi * kchi'
+      IK_REQUIRE(std::isfinite(G1[a * d + b]) && std::isfinite(G2[a * d + b]), ISOKANN_DOMAIN_PINV, msg);
+    }
+  // pinv(kchi) = kchi' V L^+ V' with kchi kchi' = V L V'; singular values sqrt(L) are cut at
+  // rtol*max with rtol = eps(Float32)*min(d,N), as LinearAlgebra.pinv does
+  double ev[kMaxD], V[kMaxD * kMaxD], G2p[kMaxD * kMaxD];
+  host_sym_eig(G2, d, ev, V);
+  double smax = 0.0;
+  for (int k = 0; k < d; ++k) smax = std::max(smax, std::sqrt(std::max(ev[k], 0.0)));
+  const double tol = 1.1920929e-07 * (double)std::min<int64_t>(d, c.N) * smax;
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b < d; ++b) {
+      double s = 0.0;
+      for (int k = 0; k < d; ++k) {
+        const double sv = std::sqrt(std::max(ev[k], 0.0));
+        if (sv > tol) s += V[a * d + k] * (1.0 / ev[k]) * V[b * d + k];
+      }
+      G2p[a * d + b] = s;
+    }
+  double Kmat[kMaxD * kMaxD];  // direct: Kinv = chi*pinv(kchi); else K = kchi*pinv(kchi)
+  const double *left = o.direct ? G1 : G2;
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b < d; ++b) {
+      double s = 0.0;
+      for (int k = 0; k < d; ++k) s += left[a * d + k] * G2p[k * d + b];
+      Kmat[a * d + b] = s;
+    }
+  float Kf_col[kMaxD * kMaxD], Zf_col[kMaxD * kMaxD];
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b < d; ++b) Kf_col[a + b * d] = (float)Kmat[a * d + b];
+  double T[kMaxD * kMaxD];
+  if (o.eigenvecs) {
+    IK_REQUIRE(host_schur_f32(Kf_col, d, Zf_col, nullptr), ISOKANN_DOMAIN_PINV, msg);
+    for (int a = 0; a < d; ++a)
+      for (int b = 0; b < d; ++b) T[a * d + b] = (double)Zf_col[a + b * d];
+  } else {
+    for (int a = 0; a < d; ++a)
+      for (int b = 0; b < d; ++b) T[a * d + b] = (a == b) ? 1.0 : 0.0;
+  }
+  double R[kMaxD * kMaxD];  // direct: Kinv; else inv(K)
+  if (o.direct) {
+    for (int i = 0; i < d * d; ++i) R[i] = (double)(float)Kmat[i];
+  } else {
+    double Kr[kMaxD * kMaxD];
+    for (int i = 0; i < d * d; ++i) Kr[i] = (double)(float)Kmat[i];
+    IK_REQUIRE(host_inverse(Kr, d, R), ISOKANN_DOMAIN_PINV, msg);
+  }
+  Mat8 mat{};
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b < d; ++b) {
+      double s = 0.0;
+      for (int k = 0; k < d; ++k) s += T[a * d + k] * R[k * d + b];
+      mat.m[a * d + b] = s;
+    }
+  finish_nd_target(c, mat, o.normalize != 0, o.permute != 0);
+}
+
+void compute_target(Ctx &c, int transform, const isokann_target_opts *opts) {
+  isokann_target_opts o{1, 0, 1, 1, 1};
+  if (opts) o = *opts;
+  compute_koopman(c);
+  c.timer.begin(KC_PHASE_TARGET, c.stream);
+  if (transform == ISOKANN_TARGET_SHIFTSCALE) {
+    IK_REQUIRE(c.d == 1, ISOKANN_BAD_ARGUMENT, "TransformShiftscale only works with one dimensional chi functions");
+    c.target.ensure((size_t)c.N);
+    int nb = 0;
+    launch_minmax(c, c.kchi.p, c.N, c.red_f.p, &nb);
+    launch_shiftscale(c, c.kchi.p, c.N, c.red_f.p, nb, c.target.p, c.flags.p);
+    set_unit_weights(c);
+    const int f = check_flags(c);
+    if (f & FLAG_CONSTANT_CHI)
+      throw ik::Error{ISOKANN_DOMAIN_CONSTANT_CHI, "Could not compute the shift-scale. chi function is constant"};
+  } else if (transform == ISOKANN_TARGET_ISA) {
+    target_isa(c, o);
+  } else if (transform == ISOKANN_TARGET_PINV) {
+    target_pinv(c, o);
+  } else {
+    throw ik::Error{ISOKANN_BAD_ARGUMENT, "unknown target transform"};
+  }
+  c.has_target = true;
+  c.timer.end(c.stream);
+}
+
+int pick_splits(const Ctx &c, int Mout, int Nout, int Kred) {
+  const int tiles = cdiv(Mout, Mout > 64 ? 128 : 64) * cdiv(Nout, Nout > 64 ? 128 : 64);
+  int s = (2 * c.num_sms + tiles - 1) / tiles;
+  const int maxs = std::max(1, Kred / 256);
+  s = std::max(1, std::min(s, maxs));
+  return std::min(s, 64);
+}
+
+// one optimiser step on the minibatch perm[start, start+len): forward, loss, backward, update
+void train_step(Ctx &c, int64_t start, int64_t len) {
+  int64_t loff, Bloc;
+  split_range(len, c.world, c.rank, &loff, &Bloc);
+  const int64_t s0 = start + loff;
+  const int L = c.L, d = c.d;
+  if (Bloc == 0) {
+    IK_CUDA(cudaMemsetAsync(c.grads.p, 0, (size_t)(c.P + 4) * sizeof(float), c.stream));
+  } else {
+    forward_rows(c, c.xs, c.perm_dev.p, s0, Bloc, true);
+    c.delta_a.ensure((size_t)Bloc * c.maxw);
+    c.delta_b.ensure((size_t)Bloc * c.maxw);
+    float *cur = c.delta_a.p, *other = c.delta_b.p;
+    launch_loss_delta(c, c.act[L].p, c.target.p, c.perm_dev.p, s0, c.w_loss.p, Bloc, d, (double)len,
+                      c.cfg.last_activation, cur, c.red_d.p, c.ticket.p, c.grads.p + c.P);
+    for (int l = L - 1; l >= 0; --l) {
+      const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
+      // weight + bias gradient: [(fin+1) x fout] = [act[l], 1]^T * delta
+      float *dest = (l == 0 && c.ln) ? c.gfold.p : c.grads.p + c.off_w[l];
+      GemmP w{};
+      w.A = c.act[l].p; w.lda = fin;
+      w.B = cur; w.ldb = fout;
+      w.M = fin + 1; w.N = fout; w.K = (int)Bloc;
+      w.ones_k = -1; w.ones_i = fin;
+      w.act = ISOKANN_ACT_IDENTITY;
+      const int splits = pick_splits(c, w.M, w.N, w.K);
+      if (splits > 1) {
+        c.splitk.ensure((size_t)splits * w.M * w.N);
+        w.C = c.splitk.p; w.ldc = fout; w.epi = EPI_PARTIAL;
+        const int used = launch_gemm(c, w, false, true, splits);
+        launch_splitk_reduce(c, c.splitk.p, used, (int64_t)w.M * w.N, dest);
+      } else {
+        w.C = dest; w.ldc = fout; w.epi = EPI_ACT;
+        launch_gemm(c, w, false, true, 1);
+      }
+      if (l > 0) {
+        // delta_{l-1} = (delta_l * W_l^T) .* act'(z_{l-1})
+        GemmP g{};
+        g.A = cur; g.lda = fout;
+        g.B = c.params.p + c.off_w[l]; g.ldb = fout;
+        g.C = other; g.ldc = fin;
+        g.Z = c.act[l].p; g.ldz = fin;
+        g.M = (int)Bloc; g.N = fin; g.K = fout;
+        g.ones_k = -1; g.ones_i = -1;
+        g.act = c.cfg.activation;
+        g.epi = EPI_MULDACT;
+        launch_gemm(c, g, true, false, 1);
+        std::swap(cur, other);
+      }
+    }
+    if (c.ln)
+      launch_unfold_ln(c, c.params.p + c.off_gamma, c.params.p + c.off_beta, c.params.p + c.off_w[0], c.gfold.p, c.F,
+                       c.cfg.widths[1], c.grads.p + c.off_gamma, c.grads.p + c.off_beta, c.grads.p + c.off_w[0],
+                       c.grads.p + c.off_b[0]);
+  }
+  if (c.world > 1) {
+    std::string err;
+    int rc = nccl_allreduce_sum_f32(c.nccl, c.comm, c.grads.p, (size_t)c.P + 2, c.stream, err);
+    IK_REQUIRE(rc == ISOKANN_OK, ISOKANN_ERR_NCCL, err);
+    c.stats.nccl_calls++;
+  }
+  launch_optimiser(c, c.P, c.beta_t[0], c.beta_t[1]);
+  if (c.cfg.optimiser == ISOKANN_OPT_ADAM) {
+    c.beta_t[0] *= c.cfg.beta1;
+    c.beta_t[1] *= c.cfg.beta2;
+  }
+  c.folded_valid = false;
+}
+
+double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool partial) {
+  IK_REQUIRE(c.xs != nullptr, ISOKANN_ERR_STATE, "no data: call isokann_set_data first");
+  IK_REQUIRE(c.has_target, ISOKANN_ERR_STATE, "no target: call isokann_target / isokann_set_target first");
+  IK_REQUIRE(perm_host != nullptr, ISOKANN_BAD_ARGUMENT, "perm must not be NULL");
+  IK_REQUIRE(minibatch >= 0, ISOKANN_BAD_ARGUMENT, "minibatch must be >= 0");
+  const int64_t N = c.N;
+  const int64_t bs = (minibatch == 0 || N < minibatch) ? N : minibatch;  // src/iso.jl:180
+  const int64_t nb = partial ? (N + bs - 1) / bs : N / bs;               // partial=false drops the tail
+  c.timer.begin(KC_PHASE_TRAIN, c.stream);
+  c.perm_raw.ensure((size_t)N);
+  c.perm_dev.ensure((size_t)N);
+  IK_CUDA(cudaMemcpyAsync(c.perm_raw.p, perm_host, (size_t)N * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+  launch_perm_to_zero_based(c, c.perm_raw.p, N, c.perm_dev.p);
+  IK_CUDA(cudaMemsetAsync(c.epoch_loss.p, 0, sizeof(double), c.stream));
+  for (int64_t i = 0; i < nb; ++i) {
+    const int64_t start = i * bs;
+    train_step(c, start, std::min(bs, N - start));
+  }
+  c.timer.end(c.stream);
+  double *lp = read_back(c, c.epoch_loss.p, 1);
+  const double ls = *lp;
+  const int f = check_flags(c);
+  if (f & FLAG_NONFINITE_LOSS)
+    throw ik::Error{ISOKANN_DOMAIN_NONFINITE_LOSS,
+                    "The ISOKANN model collapsed under training. Try reducing the learning rate or increasing "
+                    "regularization"};
+  return ls / (double)N;  // src/iso.jl:193
+}
+
+void upload_rows(Ctx &c, const void *host, bool f64, int64_t count, float *dev) {
+  if (count <= 0) return;
+  if (!f64) {
+    IK_CUDA(cudaMemcpyAsync(dev, host, (size_t)count * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    sync_stream(c);
+    return;
+  }
+  // Float64 coordinates: the reference featurizes in the input eltype and casts the features to
+  // Float32 (src/simulation.jl:112); here coordinates are rounded to Float32 on upload.
+  const int64_t blk = 1 << 22;
+  std::vector<float> tmp((size_t)std::min(blk, count));
+  const double *src = (const double *)host;
+  for (int64_t o = 0; o < count; o += blk) {
+    const int64_t n = std::min(blk, count - o);
+    for (int64_t i = 0; i < n; ++i) tmp[i] = (float)src[o + i];
+    IK_CUDA(cudaMemcpyAsync(dev + o, tmp.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    sync_stream(c);
+  }
+}
+
+void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_ptrs, int64_t D, int64_t K, int64_t N,
+                   int64_t n_off, int64_t n_loc) {
+  IK_REQUIRE(xs != nullptr, ISOKANN_BAD_ARGUMENT, "xs must not be NULL");
+  IK_REQUIRE(D == c.D, ISOKANN_BAD_ARGUMENT, "coordinate dimension does not match the featurizer/model");
+  IK_REQUIRE(N > 0 && K >= 0, ISOKANN_BAD_ARGUMENT, "N must be positive");
+  int64_t eo, el;
+  split_range(N, c.world, c.rank, &eo, &el);
+  IK_REQUIRE(n_off == eo && n_loc == el, ISOKANN_BAD_ARGUMENT,
+             "shard does not follow the contiguous split rule (see isokann_set_data_sharded)");
+  c.has_target = false;
+  c.has_weights = false;
+  c.N = N; c.K = K; c.n_off = n_off; c.n_loc = n_loc;
+  if (dev_ptrs) {
+    c.xs = (const float *)xs;
+    c.ys = (const float *)ys;
+  } else {
+    c.xs_own.ensure((size_t)N * D);
+    upload_rows(c, xs, f64, N * D, c.xs_own.p);
+    c.xs = c.xs_own.p;
+    c.ys = nullptr;
+    if (ys && K > 0 && n_loc > 0) {
+      c.ys_own.ensure((size_t)n_loc * K * D);
+      upload_rows(c, ys, f64, n_loc * K * D, c.ys_own.p);
+      c.ys = c.ys_own.p;
+    }
+  }
+}
+
+void build_pair_table(Ctx &c) {
+  const isokann_config &g = c.cfg;
+  std::vector<int2> tab;
+  auto upper = [&](const std::vector<int> &atoms) {  // column-major strict upper triangle (halfinds)
+    const int n = (int)atoms.size();
+    for (int j = 1; j < n; ++j)
+      for (int i = 0; i < j; ++i) tab.push_back(make_int2(3 * atoms[i], 3 * atoms[j]));
+  };
+  if (g.featurizer == ISOKANN_FEAT_ALLPAIRS) {
+    std::vector<int> atoms(g.n_atoms);
+    for (int i = 0; i < g.n_atoms; ++i) atoms[i] = i;
+    upper(atoms);
+  } else if (g.featurizer == ISOKANN_FEAT_ATOMS) {
+    std::vector<int> atoms;
+    for (int i = 0; i < g.n_index; ++i) {
+      IK_REQUIRE(c.index[i] >= 1 && c.index[i] <= g.n_atoms, ISOKANN_BAD_ARGUMENT, "atom index out of range");
+      atoms.push_back(c.index[i] - 1);
+    }
+    upper(atoms);
+  } else if (g.featurizer == ISOKANN_FEAT_PAIRS) {
+    for (int i = 0; i < g.n_index; ++i) {
+      const int a = c.index[2 * i], b = c.index[2 * i + 1];
+      IK_REQUIRE(a >= 1 && a <= g.n_atoms && b >= 1 && b <= g.n_atoms, ISOKANN_BAD_ARGUMENT,
+                 "pair index out of range");
+      tab.push_back(make_int2(3 * (a - 1), 3 * (b - 1)));
+    }
+  }
+  c.n_pairs = (int)tab.size();
+  if (!tab.empty()) {
+    c.pairs.ensure(tab.size());
+    IK_CUDA(cudaMemcpy(c.pairs.p, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// exported entry points
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t isokann_abi_version(void) { return ISOKANN_ABI_VERSION; }
+
+const char *isokann_last_error(const isokann_ctx *ctx) {
+  if (!ctx) return g_create_err.c_str();
+  return ctx->err.c_str();
+}
+
+int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
+  if (!cfg || !out) return ISOKANN_BAD_ARGUMENT;
+  *out = nullptr;
+  isokann_ctx *c = nullptr;
+  try {
+    IK_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= ISOKANN_MAX_LAYERS, ISOKANN_BAD_ARGUMENT, "n_layers out of range");
+    for (int l = 0; l <= cfg->n_layers; ++l)
+      IK_REQUIRE(cfg->widths[l] >= 1, ISOKANN_BAD_ARGUMENT, "layer widths must be positive");
+    IK_REQUIRE(cfg->optimiser == ISOKANN_OPT_ADAM || cfg->optimiser == ISOKANN_OPT_NESTEROV, ISOKANN_BAD_ARGUMENT,
+               "unknown optimiser");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw ik::Error{ISOKANN_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                            cudaGetErrorString(e)};
+    IK_REQUIRE(cfg->device >= 0 && cfg->device < ndev, ISOKANN_BAD_ARGUMENT, "device ordinal out of range");
+    c = new isokann_ctx;
+    c->cfg = *cfg;
+    c->dev = cfg->device;
+    IK_CUDA(cudaSetDevice(c->dev));
+    cudaDeviceProp prop;
+    IK_CUDA(cudaGetDeviceProperties(&prop, c->dev));
+    c->num_sms = prop.multiProcessorCount;
+    IK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const int nidx = cfg->featurizer == ISOKANN_FEAT_PAIRS ? 2 * cfg->n_index
+                                                           : (cfg->featurizer == ISOKANN_FEAT_ATOMS ? cfg->n_index : 0);
+    if (nidx > 0) {
+      IK_REQUIRE(cfg->index != nullptr, ISOKANN_BAD_ARGUMENT, "featurizer index list missing");
+      c->index.assign(cfg->index, cfg->index + nidx);
+    }
+    c->cfg.index = nullptr;
+    c->L = cfg->n_layers;
+    c->F = cfg->widths[0];
+    c->d = cfg->widths[c->L];
+    c->ln = cfg->layernorm != 0;
+    if (c->cfg.ln_eps <= 0.f) c->cfg.ln_eps = 1e-5f;
+    if (cfg->featurizer == ISOKANN_FEAT_IDENTITY) {
+      c->D = c->F;
+    } else {
+      IK_REQUIRE(cfg->n_atoms >= 2, ISOKANN_BAD_ARGUMENT, "n_atoms must be >= 2 for distance featurizers");
+      c->D = 3 * cfg->n_atoms;
+      build_pair_table(*c);
+      IK_REQUIRE(c->n_pairs == c->F, ISOKANN_BAD_ARGUMENT,
+                 "model input width does not match the number of pair-distance features");
+    }
+    int64_t off = 0;
+    if (c->ln) {
+      c->off_gamma = off; off += c->F;
+      c->off_beta = off; off += c->F;
+    }
+    c->maxw = 0;
+    for (int l = 0; l < c->L; ++l) {
+      const int64_t fin = cfg->widths[l], fout = cfg->widths[l + 1];
+      c->off_w.push_back(off); off += fin * fout;
+      c->off_b.push_back(off); off += fout;
+    }
+    for (int l = 0; l <= c->L; ++l) c->maxw = std::max(c->maxw, cfg->widths[l]);
+    c->P = off;
+    c->params.ensure((size_t)c->P);
+    c->grads.ensure((size_t)c->P + 4);
+    c->opt_m.ensure((size_t)c->P);
+    c->opt_v.ensure((size_t)c->P);
+    IK_CUDA(cudaMemset(c->params.p, 0, (size_t)c->P * sizeof(float)));
+    IK_CUDA(cudaMemset(c->grads.p, 0, ((size_t)c->P + 4) * sizeof(float)));
+    IK_CUDA(cudaMemset(c->opt_m.p, 0, (size_t)c->P * sizeof(float)));
+    IK_CUDA(cudaMemset(c->opt_v.p, 0, (size_t)c->P * sizeof(float)));
+    if (c->ln) {
+      const size_t seg = (size_t)(c->F + 1) * cfg->widths[1];
+      c->folded1.ensure(seg);
+      c->gfold.ensure(seg);
+    }
+    c->beta_t[0] = cfg->beta1;
+    c->beta_t[1] = cfg->beta2;
+    c->act.resize(c->L + 1);
+    c->flags.ensure(1);
+    c->ticket.ensure(1);
+    c->epoch_loss.ensure(1);
+    IK_CUDA(cudaMemset(c->flags.p, 0, sizeof(int)));
+    IK_CUDA(cudaMemset(c->ticket.p, 0, sizeof(unsigned int)));
+    IK_CUDA(cudaMemset(c->epoch_loss.p, 0, sizeof(double)));
+    c->red_f.ensure(2 * 1024);
+    c->red_d.ensure(256 * kMaxD * 2 * kMaxD + 1024);
+    c->red_am.ensure(512);
+    set_unit_weights(*c);
+    IK_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return ISOKANN_OK;
+  } catch (const ik::Error &e) {
+    g_create_err = e.msg;
+    if (c) {
+      delete c;
+    }
+    return e.code;
+  }
+}
+
+int32_t isokann_destroy(isokann_ctx *c) {
+  if (!c) return ISOKANN_OK;
+  cudaSetDevice(c->dev);
+  cudaStreamSynchronize(c->stream);
+  if (c->comm) nccl_comm_destroy(c->nccl, c->comm);
+  c->timer.destroy();
+  for (auto &a : c->act) a.release();
+  DevBuf<float> *fb[] = {&c->params, &c->grads, &c->opt_m, &c->opt_v, &c->folded1, &c->gfold, &c->xs_own, &c->ys_own,
+                         &c->kweights, &c->chi_x, &c->kchi, &c->kchi_loc, &c->gather_pad, &c->target, &c->w_loss,
+                         &c->delta_a, &c->delta_b, &c->splitk, &c->staging_in, &c->staging_out, &c->red_f};
+  for (auto *b : fb) b->release();
+  c->pairs.release();
+  c->red_d.release();
+  c->epoch_loss.release();
+  c->red_am.release();
+  c->perm_dev.release();
+  c->perm_raw.release();
+  c->flags.release();
+  c->ticket.release();
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return ISOKANN_OK;
+}
+
+int64_t isokann_num_params(const isokann_ctx *c) { return c ? c->P : -1; }
+int32_t isokann_feature_dim(const isokann_ctx *c) { return c ? c->F : -1; }
+int32_t isokann_coord_dim(const isokann_ctx *c) { return c ? c->D : -1; }
+
+int32_t isokann_comm_get_unique_id(void *id128) {
+  if (!id128) return ISOKANN_BAD_ARGUMENT;
+  std::string err;
+  Nccl *n = nccl_load(err);
+  if (!n) {
+    g_create_err = err;
+    return ISOKANN_ERR_NCCL;
+  }
+  int rc = nccl_get_unique_id(n, id128, err);
+  if (rc != ISOKANN_OK) g_create_err = err;
+  return rc;
+}
+
+int32_t isokann_comm_init(isokann_ctx *c, int32_t world, int32_t rank, const void *id128) {
+  return guarded(c, [&] {
+    IK_REQUIRE(world >= 1 && rank >= 0 && rank < world, ISOKANN_BAD_ARGUMENT, "bad world/rank");
+    IK_REQUIRE(c->xs == nullptr, ISOKANN_ERR_STATE, "isokann_comm_init must precede isokann_set_data");
+    if (world == 1) {
+      c->world = 1;
+      c->rank = 0;
+      return;
+    }
+    IK_REQUIRE(id128 != nullptr, ISOKANN_BAD_ARGUMENT, "id128 must not be NULL");
+    std::string err;
+    c->nccl = nccl_load(err);
+    IK_REQUIRE(c->nccl != nullptr, ISOKANN_ERR_NCCL, err);
+    c->comm = nccl_comm_init(c->nccl, world, rank, id128, err);
+    IK_REQUIRE(c->comm != nullptr, ISOKANN_ERR_NCCL, err);
+    c->world = world;
+    c->rank = rank;
+  });
+}
+
+int32_t isokann_set_data(isokann_ctx *c, const float *xs, const float *ys, int64_t D, int64_t K, int64_t N) {
+  return guarded(c, [&] {
+    IK_REQUIRE(c->world == 1, ISOKANN_ERR_STATE, "use isokann_set_data_sharded on a multi-rank context");
+    set_data_impl(*c, xs, ys, false, false, D, K, N, 0, N);
+  });
+}
+
+int32_t isokann_set_data_f64(isokann_ctx *c, const double *xs, const double *ys, int64_t D, int64_t K, int64_t N) {
+  return guarded(c, [&] {
+    IK_REQUIRE(c->world == 1, ISOKANN_ERR_STATE, "use isokann_set_data_sharded on a multi-rank context");
+    set_data_impl(*c, xs, ys, true, false, D, K, N, 0, N);
+  });
+}
+
+int32_t isokann_set_data_sharded(isokann_ctx *c, const float *xs, const float *ys_local, int64_t D, int64_t K,
+                                 int64_t N, int64_t n_offset, int64_t n_local) {
+  return guarded(c, [&] { set_data_impl(*c, xs, ys_local, false, false, D, K, N, n_offset, n_local); });
+}
+
+int32_t isokann_set_data_dev(isokann_ctx *c, const float *dev_xs, const float *dev_ys_local, int64_t D, int64_t K,
+                             int64_t N, int64_t n_offset, int64_t n_local) {
+  return guarded(c, [&] { set_data_impl(*c, dev_xs, dev_ys_local, false, true, D, K, N, n_offset, n_local); });
+}
+
+int32_t isokann_set_koopman_weights(isokann_ctx *c, const float *w) {
+  return guarded(c, [&] {
+    if (!w) {
+      c->has_weights = false;
+      return;
+    }
+    IK_REQUIRE(c->ys != nullptr, ISOKANN_ERR_STATE, "no Koopman samples resident");
+    c->kweights.ensure((size_t)c->n_loc * c->K);
+    IK_CUDA(cudaMemcpyAsync(c->kweights.p, w, (size_t)c->n_loc * c->K * sizeof(float), cudaMemcpyHostToDevice,
+                            c->stream));
+    sync_stream(*c);
+    c->has_weights = true;
+  });
+}
+
+int32_t isokann_upload_params(isokann_ctx *c, const float *flat, int64_t P) {
+  return guarded(c, [&] {
+    IK_REQUIRE(flat && P == c->P, ISOKANN_BAD_ARGUMENT, "parameter count mismatch");
+    IK_CUDA(cudaMemcpyAsync(c->params.p, flat, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    sync_stream(*c);
+    c->folded_valid = false;
+  });
+}
+
+int32_t isokann_download_params(isokann_ctx *c, float *flat, int64_t P) {
+  return guarded(c, [&] {
+    IK_REQUIRE(flat && P == c->P, ISOKANN_BAD_ARGUMENT, "parameter count mismatch");
+    IK_CUDA(cudaMemcpyAsync(flat, c->params.p, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    sync_stream(*c);
+  });
+}
+
+int32_t isokann_upload_opt_state(isokann_ctx *c, const float *m, const float *v, const float *beta_t, int64_t P) {
+  return guarded(c, [&] {
+    IK_REQUIRE(m && P == c->P, ISOKANN_BAD_ARGUMENT, "optimiser state size mismatch");
+    IK_CUDA(cudaMemcpyAsync(c->opt_m.p, m, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (c->cfg.optimiser == ISOKANN_OPT_ADAM) {
+      IK_REQUIRE(v && beta_t, ISOKANN_BAD_ARGUMENT, "Adam state needs v and beta_t");
+      IK_CUDA(cudaMemcpyAsync(c->opt_v.p, v, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      c->beta_t[0] = beta_t[0];
+      c->beta_t[1] = beta_t[1];
+    }
+    sync_stream(*c);
+  });
+}
+
+int32_t isokann_download_opt_state(isokann_ctx *c, float *m, float *v, float *beta_t, int64_t P) {
+  return guarded(c, [&] {
+    IK_REQUIRE(m && P == c->P, ISOKANN_BAD_ARGUMENT, "optimiser state size mismatch");
+    IK_CUDA(cudaMemcpyAsync(m, c->opt_m.p, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (c->cfg.optimiser == ISOKANN_OPT_ADAM) {
+      if (v) IK_CUDA(cudaMemcpyAsync(v, c->opt_v.p, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      if (beta_t) {
+        beta_t[0] = c->beta_t[0];
+        beta_t[1] = c->beta_t[1];
+      }
+    }
+    sync_stream(*c);
+  });
+}
+
+int32_t isokann_featurize(isokann_ctx *c, const float *coords, int64_t D, int64_t M, float *features_out) {
+  return guarded(c, [&] {
+    IK_REQUIRE(coords && features_out, ISOKANN_BAD_ARGUMENT, "NULL buffer");
+    IK_REQUIRE(D == c->D, ISOKANN_BAD_ARGUMENT, "coordinate dimension does not match the featurizer");
+    const int64_t ch = chunk_rows(*c, 1);
+    c->staging_in.ensure((size_t)std::min(ch, std::max<int64_t>(M, 1)) * D);
+    c->staging_out.ensure((size_t)std::min(ch, std::max<int64_t>(M, 1)) * c->F);
+    const bool pairs = c->cfg.featurizer != ISOKANN_FEAT_IDENTITY;
+    for (int64_t m0 = 0; m0 < M; m0 += ch) {
+      const int64_t m = std::min(ch, M - m0);
+      IK_CUDA(cudaMemcpyAsync(c->staging_in.p, coords + m0 * D, (size_t)m * D * sizeof(float), cudaMemcpyHostToDevice,
+                              c->stream));
+      launch_featurize(*c, c->staging_in.p, nullptr, 0, m, pairs, false, c->staging_out.p, c->F);
+      IK_CUDA(cudaMemcpyAsync(features_out + m0 * c->F, c->staging_out.p, (size_t)m * c->F * sizeof(float),
+                              cudaMemcpyDeviceToHost, c->stream));
+      sync_stream(*c);
+    }
+  });
+}
+
+int32_t isokann_forward(isokann_ctx *c, const float *in, int64_t rows, int64_t M, int32_t is_features,
+                        float *chi_out) {
+  return guarded(c, [&] {
+    IK_REQUIRE(in && chi_out, ISOKANN_BAD_ARGUMENT, "NULL buffer");
+    const bool coords = !is_features;
+    IK_REQUIRE(rows == (coords ? c->D : c->F), ISOKANN_BAD_ARGUMENT, "row count does not match the model input");
+    const int64_t ch = chunk_rows(*c, 1);
+    c->staging_in.ensure((size_t)std::min(ch, std::max<int64_t>(M, 1)) * rows);
+    for (int64_t m0 = 0; m0 < M; m0 += ch) {
+      const int64_t m = std::min(ch, M - m0);
+      IK_CUDA(cudaMemcpyAsync(c->staging_in.p, in + m0 * rows, (size_t)m * rows * sizeof(float),
+                              cudaMemcpyHostToDevice, c->stream));
+      forward_rows(*c, c->staging_in.p, nullptr, 0, m, coords);
+      IK_CUDA(cudaMemcpyAsync(chi_out + m0 * c->d, c->act[c->L].p, (size_t)m * c->d * sizeof(float),
+                              cudaMemcpyDeviceToHost, c->stream));
+      sync_stream(*c);
+    }
+    c->timer.flush(c->stream);
+  });
+}
+
+int32_t isokann_chis(isokann_ctx *c, float *chi_out) {
+  return guarded(c, [&] {
+    compute_chis(*c);
+    if (chi_out)
+      IK_CUDA(cudaMemcpyAsync(chi_out, c->chi_x.p, (size_t)c->N * c->d * sizeof(float), cudaMemcpyDeviceToHost,
+                              c->stream));
+    sync_stream(*c);
+    c->timer.flush(c->stream);
+  });
+}
+
+int32_t isokann_koopman(isokann_ctx *c, float *kchi_out) {
+  return guarded(c, [&] {
+    compute_koopman(*c);
+    if (kchi_out)
+      IK_CUDA(cudaMemcpyAsync(kchi_out, c->kchi.p, (size_t)c->N * c->d * sizeof(float), cudaMemcpyDeviceToHost,
+                              c->stream));
+    sync_stream(*c);
+    c->timer.flush(c->stream);
+  });
+}
+
+int32_t isokann_target(isokann_ctx *c, int32_t transform, const isokann_target_opts *opts, float *target_out) {
+  return guarded(c, [&] {
+    compute_target(*c, transform, opts);
+    if (target_out)
+      IK_CUDA(cudaMemcpyAsync(target_out, c->target.p, (size_t)c->N * c->d * sizeof(float), cudaMemcpyDeviceToHost,
+                              c->stream));
+    sync_stream(*c);
+    c->timer.flush(c->stream);
+  });
+}
+
+int32_t isokann_set_target(isokann_ctx *c, const float *target, int64_t d, int64_t N) {
+  return guarded(c, [&] {
+    IK_REQUIRE(target && d == c->d && N == c->N, ISOKANN_BAD_ARGUMENT, "target shape mismatch");
+    c->target.ensure((size_t)N * d);
+    IK_CUDA(cudaMemcpyAsync(c->target.p, target, (size_t)N * d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (d == 1) {
+      set_unit_weights(*c);
+    } else {
+      IK_REQUIRE(d <= kMaxD, ISOKANN_BAD_ARGUMENT, "chi dimension exceeds ISOKANN_MAX_D");
+      Mat8 id{};
+      for (int a = 0; a < d; ++a) id.m[a * d + a] = 1.0;
+      // identity apply in place: recomputes the loss weights 1 ./ std(target, dims=2)
+      c->kchi.ensure((size_t)N * d);
+      IK_CUDA(cudaMemcpyAsync(c->kchi.p, c->target.p, (size_t)N * d * sizeof(float), cudaMemcpyDeviceToDevice,
+                              c->stream));
+      finish_nd_target(*c, id, false, false);
+    }
+    sync_stream(*c);
+    c->has_target = true;
+  });
+}
+
+int32_t isokann_train_epoch(isokann_ctx *c, const int64_t *perm, int64_t minibatch, int32_t partial,
+                            double *loss_out) {
+  return guarded(c, [&] {
+    const double l = train_epoch(*c, perm, minibatch, partial != 0);
+    if (loss_out) *loss_out = l;
+    c->timer.flush(c->stream);
+  });
+}
+
+int32_t isokann_iterate(isokann_ctx *c, int32_t transform, const isokann_target_opts *opts, int64_t n_iter,
+                        int64_t epochs, int64_t minibatch, const int64_t *perms, double *losses_out) {
+  return guarded(c, [&] {
+    IK_REQUIRE(perms != nullptr, ISOKANN_BAD_ARGUMENT, "perms must not be NULL");
+    int64_t k = 0;
+    for (int64_t it = 0; it < n_iter; ++it) {
+      compute_target(*c, transform, opts);
+      for (int64_t e = 0; e < epochs; ++e, ++k) {
+        const double l = train_epoch(*c, perms + k * c->N, minibatch, false);
+        if (losses_out) losses_out[k] = l;
+      }
+    }
+    c->timer.flush(c->stream);
+  });
+}
+
+int32_t isokann_enable_timing(isokann_ctx *c, int32_t on) {
+  return guarded(c, [&] {
+    c->timer.flush(c->stream);
+    c->timer.enabled = on != 0;
+  });
+}
+
+int32_t isokann_get_stats(isokann_ctx *c, isokann_stats *out) {
+  return guarded(c, [&] {
+    IK_REQUIRE(out != nullptr, ISOKANN_BAD_ARGUMENT, "NULL stats");
+    c->timer.flush(c->stream);
+    c->stats.ms_featurize = c->timer.ms[KC_FEATURIZE];
+    c->stats.ms_gemm = c->timer.ms[KC_GEMM];
+    c->stats.ms_reduce = c->timer.ms[KC_REDUCE];
+    c->stats.ms_train_elementwise = c->timer.ms[KC_TRAIN_EW];
+    c->stats.ms_optimiser = c->timer.ms[KC_OPT];
+    c->stats.ms_koopman_total = c->timer.ms[KC_PHASE_KOOPMAN];
+    c->stats.ms_target_total = c->timer.ms[KC_PHASE_TARGET];
+    c->stats.ms_train_total = c->timer.ms[KC_PHASE_TRAIN];
+    *out = c->stats;
+  });
+}
+
+int32_t isokann_reset_stats(isokann_ctx *c) {
+  return guarded(c, [&] {
+    c->timer.flush(c->stream);
+    for (double &m : c->timer.ms) m = 0.0;
+    c->stats = isokann_stats{};
+  });
+}
+
+int32_t isokann_synchronize(isokann_ctx *c) {
+  return guarded(c, [&] { sync_stream(*c); });
+}
+
+void *isokann_stream(isokann_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int32_t isokann_host_schur(const float *a_colmajor, int32_t d, float *z_colmajor, float *t_colmajor) {
+  if (!a_colmajor || !z_colmajor || d < 1 || d > kMaxD) return ISOKANN_BAD_ARGUMENT;
+  return host_schur_f32(a_colmajor, d, z_colmajor, t_colmajor) ? ISOKANN_OK : ISOKANN_DOMAIN_PINV;
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+// Shared declarations of libisokann_b200: context, error handling, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/isokann_b200.h"
+
+namespace ik {
+
+struct Error {
+  int32_t code;
+  std::string msg;
+};
+
+#define IK_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      throw ik::Error{ISOKANN_ERR_CUDA, std::string(#expr) + " -> " + cudaGetErrorString(e__)};    \
+  } while (0)
+
+#define IK_REQUIRE(cond, code, text)            \
+  do {                                          \
+    if (!(cond)) throw ik::Error{(code), (text)}; \
+  } while (0)
+
+constexpr int kMaxD = 8;  // largest chi dimension handled by the N-D target kernels
+
+// device-side error flags (sticky until read by the host)
+enum : int { FLAG_CONSTANT_CHI = 1, FLAG_NONFINITE_LOSS = 2 };
+
+// kernel classes for the event timers
+enum KClass {
+  KC_FEATURIZE = 0, KC_GEMM = 1, KC_REDUCE = 2, KC_TRAIN_EW = 3, KC_OPT = 4,
+  KC_PHASE_KOOPMAN = 5, KC_PHASE_TARGET = 6, KC_PHASE_TRAIN = 7, KC_COUNT = 8
+};
+
+struct EventTimer {
+  struct Pair {
+    cudaEvent_t a, b;
+    int cls;
+  };
+  bool enabled = false;
+  std::vector<Pair> pool;
+  size_t used = 0;
+  std::vector<size_t> open;
+  double ms[KC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void begin(int cls, cudaStream_t s);  // pairs may nest (phase around kernels)
+  void end(cudaStream_t s);
+  void flush(cudaStream_t s);  // synchronises the stream and accumulates elapsed times
+  void destroy();
+};
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void ensure(size_t count) {
+    if (count <= n) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    IK_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct Mat8 {
+  double m[kMaxD * kMaxD];  // row-major d x d
+};
+
+// replay record of the inner-simplex row transformation (PCCAPlus indexmap)
+struct IsaReplay {
+  double pre[kMaxD * kMaxD];   // whitening matrix W (row-major), identity if none: x <- x * W
+  double x0[kMaxD];            // translation (row selected in round 1, after pre-multiplication)
+  double r[kMaxD];             // r[j]  : divisor of round j (j >= 1)
+  double v[kMaxD][kMaxD];      // v[j]  : unit row projected out in round j (j >= 1)
+  int rounds;                  // number of completed rounds
+  int d;
+};
+
+struct ArgmaxPartial {
+  double val;
+  long long idx;
+};
+
+// ---- kernel launch wrappers (defined in the .cu files) ----
+struct GemmP {
+  const float *A;
+  int64_t lda;
+  const float *B;
+  int64_t ldb;
+  float *C;
+  int64_t ldc;
+  const float *Z;  // EPI_MULDACT: activation outputs the derivative is taken at
+  int64_t ldz;
+  int M, N, K;     // logical extents (including an augmented ones index if used)
+  int ones_k;      // A(i, ones_k) := 1 (bias row of the forward pass), -1 = none
+  int ones_i;      // A(ones_i, k) := 1 (bias row of the weight gradient), -1 = none
+  int kchunk;      // K range per blockIdx.z (split-K); == K rounded up when gridDim.z == 1
+  int act;         // activation id for the epilogue
+  int epi;         // 0: C = act(acc); 1: C = acc * dact(Z); 2: raw split-K partial at C + z*M*N
+};
+enum { EPI_ACT = 0, EPI_MULDACT = 1, EPI_PARTIAL = 2 };
+
+struct Ctx;
+
+void launch_featurize(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M, bool pairs,
+                      bool do_ln, float *out, int64_t ldo);
+int launch_gemm(Ctx &c, const GemmP &p, bool a_kcontig, bool b_jcontig, int splits);  // returns splits used
+void launch_splitk_reduce(Ctx &c, const float *partials, int splits, int64_t count, float *out);
+void launch_kmean(Ctx &c, const float *chi, const float *weights, int64_t n, int K, int d, float *out);
+void launch_minmax(Ctx &c, const float *x, int64_t n, float *partials, int *nblocks_out);
+void launch_shiftscale(Ctx &c, const float *x, int64_t n, const float *partials, int nblocks, float *out, int *flags);
+void launch_fill(Ctx &c, float *x, int64_t n, float v);
+void launch_gram(Ctx &c, const float *chi, const float *kchi, int64_t n, int d, double *partials, int *nblocks_out);
+void launch_apply(Ctx &c, int mode, const float *kchi, const float *chi, int64_t n, int d, const Mat8 &mat,
+                  float *target_out, double *partials, int *nblocks_out);
+void launch_isa_argmax(Ctx &c, const float *kchi, int64_t n, const IsaReplay &rp, ArgmaxPartial *partials,
+                       int *nblocks_out);
+void launch_loss_delta(Ctx &c, const float *chi, const float *target, const int64_t *idx, int64_t idx_off,
+                       const float *w, int64_t Bloc, int d, double Bglobal, int lastact, float *delta,
+                       double *partials, unsigned int *ticket, float *packed_tail);
+void launch_fold_ln(Ctx &c, const float *gamma, const float *beta, const float *W1, const float *b1, int F, int h1,
+                    float *folded);
+void launch_unfold_ln(Ctx &c, const float *gamma, const float *beta, const float *W1, const float *gfold, int F,
+                      int h1, float *g_gamma, float *g_beta, float *g_W1, float *g_b1);
+void launch_optimiser(Ctx &c, int64_t P, float bt1, float bt2);
+void launch_perm_to_zero_based(Ctx &c, const int64_t *perm1, int64_t n, int64_t *out0);
+void launch_compact_gather(Ctx &c, const float *padded, int world, int64_t nmax, int64_t N, int d, float *out);
+
+double isa_row_norm_host(const float *row, const IsaReplay &rp, double *xout);
+
+// host-side small dense algebra (hostlinalg.cpp)
+bool host_inverse(const double *a_rowmajor, int d, double *inv_rowmajor);
+void host_sym_eig(const double *a_rowmajor, int d, double *evals, double *evecs_rowmajor);
+bool host_schur_f32(const float *a_colmajor, int d, float *z_colmajor, float *t_colmajor);
+
+// dynamically loaded NCCL (nccl_dyn.cpp)
+struct Nccl;
+Nccl *nccl_load(std::string &err);
+int nccl_get_unique_id(Nccl *n, void *id128, std::string &err);
+void *nccl_comm_init(Nccl *n, int world, int rank, const void *id128, std::string &err);
+void nccl_comm_destroy(Nccl *n, void *comm);
+int nccl_allreduce_sum_f32(Nccl *n, void *comm, float *buf, size_t count, cudaStream_t s, std::string &err);
+int nccl_allgather_f32(Nccl *n, void *comm, const float *send, float *recv, size_t count_per_rank, cudaStream_t s,
+                       std::string &err);
+
+struct Ctx {
+  isokann_config cfg{};
+  std::vector<int32_t> index;
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  int L = 0, F = 0, D = 0, d = 0, maxw = 0;
+  int64_t P = 0;
+  bool ln = false;
+  int64_t off_gamma = -1, off_beta = -1;
+  std::vector<int64_t> off_w, off_b;  // offsets into the flat parameter vector
+
+  // parameters, gradients (+4 tail floats: packed step loss), optimiser state
+  DevBuf<float> params, grads, opt_m, opt_v, folded1, gfold;
+  float beta_t[2] = {0.f, 0.f};
+  bool folded_valid = false;  // folded1 matches the current parameters
+  DevBuf<int2> pairs;  // coordinate offsets (3a, 3b) per feature
+  int n_pairs = 0;
+
+  // resident data
+  DevBuf<float> xs_own, ys_own, kweights;
+  const float *xs = nullptr, *ys = nullptr;
+  int64_t N = 0, K = 0, n_off = 0, n_loc = 0;
+  bool has_weights = false;
+  DevBuf<float> chi_x, kchi, kchi_loc, gather_pad, target, w_loss;
+  bool has_target = false;
+
+  // workspaces
+  std::vector<DevBuf<float>> act;  // act[l]: rows x widths[l]
+  DevBuf<float> delta_a, delta_b, splitk, staging_in, staging_out, red_f;
+  DevBuf<double> red_d, epoch_loss;
+  DevBuf<ArgmaxPartial> red_am;
+  DevBuf<int64_t> perm_dev, perm_raw;
+  DevBuf<int> flags;
+  DevBuf<unsigned int> ticket;
+  int64_t act_rows = 0;
+  void *pinned = nullptr;  // small pinned host scratch for reductions read back
+  size_t pinned_bytes = 0;
+
+  // multi-GPU
+  Nccl *nccl = nullptr;
+  void *comm = nullptr;
+  int world = 1, rank = 0;
+
+  // accounting
+  isokann_stats stats{};
+  EventTimer timer;
+  std::string err;
+
+  void count_launch(int cls, double flops_or_bytes = 0.0) {
+    stats.kernel_launches++;
+    if (cls == KC_GEMM) {
+      stats.n_gemm_launches++;
+      if (timer.enabled) stats.gemm_flops += flops_or_bytes;
+    }
+    if (cls == KC_FEATURIZE) {
+      stats.n_featurize_launches++;
+      if (timer.enabled) stats.featurize_bytes += flops_or_bytes;
+    }
+  }
+};
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace ik

@@ -1,0 +1,44 @@
+"""Host-side sharding plan for one-process-per-GPU runs (nothing to mirror in
+the reference, which is single-device).
+
+Start points n (with their K Koopman samples) are split contiguously over ranks for the
+featurize -> chi -> K-mean pass; every minibatch ``perm[i*B:(i+1)*B]`` is split contiguously
+over ranks for the training step.  Both use the same rule as the library
+(``split_range`` in csrc/api.cu); these helpers are what the host uses to slice ``ys`` and what
+the gloo tests check.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """contiguous split of [0, n): returns (offset, length) of ``rank``; the first n % world
+    ranks get one extra element."""
+    base, rem = divmod(n, world)
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+
+
+def batch_bounds(n: int, minibatch: int, partial: bool = False):
+    """(start, length) of every minibatch of an epoch: batchsize rule of src/iso.jl:180 and the
+    dropped tail of DataLoader(partial=false) (src/iso.jl:181)."""
+    bs = n if (minibatch == 0 or n < minibatch) else minibatch
+    nb = -(-n // bs) if partial else n // bs
+    return [(i * bs, min(bs, n - i * bs)) for i in range(nb)]
+
+
+def rank_batch_slice(perm1: np.ndarray, start: int, length: int, world: int, rank: int) -> np.ndarray:
+    """the 1-based sample ids of minibatch [start, start+length) that ``rank`` processes"""
+    off, n = shard_range(length, world, rank)
+    return np.asarray(perm1[start + off:start + off + n])
+
+
+def broadcast_unique_id(rank: int, src: int = 0) -> Optional[bytes]:
+    """rank ``src`` creates the NCCL unique id, torch.distributed broadcasts it to everyone"""
+    import torch.distributed as dist
+    from .engine import Engine
+    box = [Engine.unique_id() if rank == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
