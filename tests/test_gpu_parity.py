@@ -1,0 +1,318 @@
+"""Parity of the CUDA path (called through the C ABI) against the oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-5 relative on distances, 1e-4 on chi after one
+iteration; the loss curve is tracked over 100 iterations.  Minibatch permutations are inputs
+shared by both sides, hence identical by construction.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from tests.helpers import make_iso, oracle_features, oracle_model, records, run_pair
+
+pytestmark = pytest.mark.gpu
+
+RTOL_DIST = 1e-5
+TOL_CHI = 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# featurizer
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,M", [("c1", 1), ("c1", 257), ("c3", 1000)])
+def test_flatpairdists_matches_oracle(pkg, oracle, name, M):
+    w = pkg.synthetic.WORKLOADS[name]
+    xs, _ = pkg.synthetic.make_data(w, M, 1)
+    got = pkg.flatpairdists(xs)                          # (F, M)
+    ref = oracle.flatpairdists(records(xs))              # (M, F)
+    assert got.shape == (w.F, M) and got.dtype == np.float32
+    assert np.allclose(records(got), ref, rtol=RTOL_DIST, atol=0)
+    assert (got >= 0).all()
+
+
+def test_flatpairdists_3d_input_and_float64(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    xs, ys = pkg.synthetic.make_data(w, 33, 3, dtype=np.float64)
+    got = pkg.flatpairdists(ys)                          # (F, K, N)
+    assert got.shape == (231, 3, 33)
+    ref = oracle.flatpairdists(records(ys))              # (N, K, F) from float64 coordinates
+    assert np.allclose(records(got), ref, rtol=RTOL_DIST)
+
+
+def test_features_atoms_and_pairs(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    xs, _ = pkg.synthetic.make_data(w, 50, 1)
+    atoms = [2, 5, 7, 9, 15, 17, 19]
+    got = pkg.FeaturesAtoms(atoms)(xs)
+    ref = oracle.flatpairdists(records(xs), atoms)
+    assert np.allclose(records(got), ref, rtol=RTOL_DIST)
+    pairs = [(1, 22), (5, 7), (9, 15), (15, 9), (3, 3)]   # row order = list order; (3,3) -> 0
+    got = pkg.pdists(xs, pairs)
+    ref = oracle.pdists(records(xs), pairs)
+    assert np.allclose(records(got), ref, rtol=RTOL_DIST)
+    assert (got[4] == 0).all()
+
+
+def test_rigid_motion_invariance_full_size(pkg):
+    # size-independent property at BASELINE size (villin-shaped, 1e5 records)
+    w = pkg.synthetic.WORKLOADS["c3"]
+    xs, _ = pkg.synthetic.make_data(w, 100_000, 1)
+    rng = np.random.default_rng(0)
+    Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    moved = (records(xs).reshape(-1, 35, 3).astype(np.float64) @ Q.T + rng.normal(size=3)).reshape(-1, 105)
+    a = pkg.flatpairdists(xs)
+    b = pkg.flatpairdists(np.asfortranarray(moved.astype(np.float32).T))
+    assert np.allclose(a, b, rtol=0, atol=2e-5)          # coordinates are rounded to fp32 after the motion
+
+
+# ---------------------------------------------------------------------------------------------
+# model forward / Koopman expectation
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1", "c2", "c3"])
+def test_chi_forward_and_koopman(pkg, oracle, name):
+    w = pkg.synthetic.WORKLOADS[name]
+    N, K = 300, 4
+    xs, ys = pkg.synthetic.make_data(w, N, K)
+    om = oracle_model(oracle, w.widths, w.layernorm, 5)
+    if w.layernorm:  # non-trivial affine so the folding is exercised
+        rng = np.random.default_rng(9)
+        om.ln_scale = rng.uniform(0.5, 1.5, w.F).astype(np.float32)
+        om.ln_bias = (0.1 * rng.normal(size=w.F)).astype(np.float32)
+    iso = make_iso(pkg, w, xs, ys, oracle.flatten_params(om))
+    xsf, ysf = oracle_features(oracle, w, xs, ys)
+    assert np.allclose(records(pkg.chis(iso)), oracle.forward(om, xsf), rtol=TOL_CHI, atol=1e-5)
+    assert np.allclose(records(pkg.chicoords(iso, xs[:, :17])), oracle.forward(om, xsf[:17]), rtol=TOL_CHI, atol=1e-5)
+    assert np.allclose(records(pkg.koopman(iso)), oracle.expectation(om, ysf), rtol=TOL_CHI, atol=1e-5)
+
+
+def test_chunking_does_not_change_results(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    xs, ys = pkg.synthetic.make_data(w, 500, 5)
+    flat = oracle.flatten_params(oracle_model(oracle, w.widths, True, 5))
+    a = make_iso(pkg, w, xs, ys, flat)
+    b = make_iso(pkg, w, xs, ys, flat, chunk=35)          # many ragged chunks (rounded to multiples of K)
+    assert np.array_equal(pkg.koopman(a), pkg.koopman(b))
+    assert np.array_equal(pkg.chis(a), pkg.chis(b))
+
+
+def test_weighted_expectation(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    N, K = 64, 5
+    xs, ys = pkg.synthetic.make_data(w, N, K)
+    om = oracle_model(oracle, w.widths, True, 5)
+    wts = np.random.default_rng(1).uniform(0.5, 1.5, size=(K, N)).astype(np.float32)
+    data = pkg.SimulationData(xs, ys, featurizer=pkg.FeaturesAll(), weights=wts)
+    iso = pkg.Iso(data, model=pkg.Chain(list(w.widths), True).load_flat(oracle.flatten_params(om)))
+    _, ysf = oracle_features(oracle, w, xs, ys)
+    ref = oracle.weighted_expectation(om, ysf, records(wts))
+    assert np.allclose(records(pkg.koopman(iso)), ref, rtol=TOL_CHI, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# targets
+# ---------------------------------------------------------------------------------------------
+def test_shiftscale_target_and_constant_chi(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    xs, ys = pkg.synthetic.make_data(w, 200, 5)
+    om = oracle_model(oracle, w.widths, True, 5)
+    iso = make_iso(pkg, w, xs, ys, oracle.flatten_params(om))
+    t = pkg.isotarget(iso)
+    xsf, ysf = oracle_features(oracle, w, xs, ys)
+    ref = oracle.isotarget_shiftscale(om, xsf, ysf)
+    assert t.shape == (1, 200)
+    assert t.min() == 0.0 and t.max() == 1.0
+    assert np.allclose(records(t), ref, atol=2e-4)
+    # all-zero parameters -> chi is constant -> DomainError like src/isotarget.jl:39
+    iso.engine.upload_params(np.zeros(iso.engine.P, np.float32))
+    with pytest.raises(pkg.DomainError) as e:
+        pkg.isotarget(iso)
+    assert e.value.code == 1
+    # shiftscale on a multi-dimensional chi is rejected (src/isotarget.jl:37)
+    w3 = copy.deepcopy(w)
+    w3.widths = [231, 38, 6, 2]
+    iso2 = make_iso(pkg, w3, xs, ys, oracle.flatten_params(oracle_model(oracle, w3.widths, True, 5)), target="isa")
+    with pytest.raises(pkg.IsokannError):
+        pkg.isotarget(iso2, pkg.TransformShiftscale())
+
+
+@pytest.mark.parametrize("d", [2, 3])
+@pytest.mark.parametrize("kind,kw", [("isa", {}), ("isa", {"whitening": True}), ("isa", {"permute": False}),
+                                     ("pinv", {}), ("pinv", {"eigenvecs": False}),
+                                     ("pinv", {"normalize": False, "permute": False})])
+def test_nd_targets(pkg, oracle, d, kind, kw):
+    w = copy.deepcopy(pkg.synthetic.WORKLOADS["c4"])
+    w.widths = [231, 38, 6, d]
+    N, K = 400, 4
+    xs, ys = pkg.synthetic.make_data(w, N, K)
+    om = oracle_model(oracle, w.widths, True, 11)
+    iso = make_iso(pkg, w, xs, ys, oracle.flatten_params(om), target=kind)
+    tobj = pkg.TransformISA(**kw) if kind == "isa" else pkg.TransformPseudoInv(**kw)
+    t = records(pkg.isotarget(iso, tobj))
+    xsf, ysf = oracle_features(oracle, w, xs, ys)
+    ref = oracle.isotarget(kind, om, xsf, ysf, **kw)
+    scale = np.abs(ref).max()
+    assert np.allclose(t, ref, rtol=2e-3, atol=2e-3 * scale), np.abs(t - ref).max() / scale
+    if kind == "isa" and not kw.get("whitening"):
+        # the d selected samples map to unit vectors (src/isotarget.jl:93,104)
+        ks = oracle.expectation(om, ysf)
+        ind = oracle.indexmap(ks.astype(np.float64))
+        rows = np.sort(t[ind], axis=1)
+        assert np.allclose(rows[:, -1], 1, atol=1e-4) and np.allclose(rows[:, :-1], 0, atol=1e-4)
+
+
+def test_user_defined_target(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    xs, ys = pkg.synthetic.make_data(w, 100, 5)
+    flat = oracle.flatten_params(oracle_model(oracle, w.widths, True, 5))
+    iso = make_iso(pkg, w, xs, ys, flat)
+
+    def custom(i):  # what scripts adding their own isotarget methods do (scripts/251126_carsten/main.jl:132)
+        k = pkg.koopman(i)
+        return (k - k.mean()) / k.std()
+    iso.target = custom
+    pkg.run_(iso, 2)
+    assert len(iso.losses) == 2 and np.isfinite(iso.losses).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# training
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("opt", ["nesterov", "adam"])
+@pytest.mark.parametrize("name", ["c1", "c2"])
+def test_one_iteration_parity(pkg, oracle, name, opt):
+    r = run_pair(pkg, oracle, name, N=256, K=4, minibatch=64, n_iter=1, opt=opt)
+    assert np.allclose(r["target_lib"], r["target_ref"], atol=2e-4)
+    assert np.allclose(r["loss_lib"], r["loss_ref"], rtol=1e-4)
+    assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=TOL_CHI, atol=TOL_CHI)
+    scale = np.abs(r["flat_ref"]).max()
+    assert np.abs(r["flat_lib"] - r["flat_ref"]).max() < 1e-4 * scale
+    assert r["stats"]["kernel_launches"] > 0
+
+
+def test_first_step_gradient_through_params(pkg, oracle):
+    # Nesterov's first step from zero state is theta - (1+rho)*eta*(g + lambda*theta): recover g exactly
+    w = pkg.synthetic.WORKLOADS["c1"]
+    N = 96
+    xs, ys = pkg.synthetic.make_data(w, N, 3)
+    om = oracle_model(oracle, w.widths, True, 5)
+    rng = np.random.default_rng(2)
+    om.ln_scale = rng.uniform(0.5, 1.5, w.F).astype(np.float32)
+    om.ln_bias = (0.1 * rng.normal(size=w.F)).astype(np.float32)
+    flat0 = oracle.flatten_params(om)
+    iso = make_iso(pkg, w, xs, ys, flat0, minibatch=0)
+    pkg.isotarget(iso)
+    perm = np.arange(1, N + 1)
+    pkg.train_batch_(iso, perm)
+    g_lib = (flat0 - iso.engine.download_params()) / (1.9e-3) - 1e-4 * flat0
+    xsf, ysf = oracle_features(oracle, w, xs, ys)
+    t = oracle.isotarget_shiftscale(om, xsf, ysf)
+    _, g_ref = oracle.batch_loss_and_grad(om, xsf, t, None)
+    # parameters are O(0.1), the step O(1e-3 * g): the recovered gradient carries ~1e-4 relative noise
+    assert np.abs(g_lib - g_ref).max() < 2e-3 * np.abs(g_ref).max() + 1e-5
+
+
+def test_epoch_bookkeeping_tail_dropped_and_partial(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    N = 250
+    xs, ys = pkg.synthetic.make_data(w, N, 2)
+    om = oracle_model(oracle, w.widths, True, 5)
+    flat0 = oracle.flatten_params(om)
+    perm = pkg.synthetic.make_perms(w, N, 1)[0]
+    xsf, ysf = oracle_features(oracle, w, xs, ys)
+    for partial in (False, True):
+        iso = make_iso(pkg, w, xs, ys, flat0, minibatch=100)
+        pkg.isotarget(iso)
+        iso.engine.reset_stats()
+        loss = pkg.train_batch_(iso, perm, partial=partial)
+        m = om.copy()
+        cfg = oracle.OptConfig()
+        t = oracle.isotarget_shiftscale(m, xsf, ysf)
+        ref = oracle.train_batch(m, xsf, t, cfg, oracle.opt_init(cfg, flat0.size), 100, perm, partial=partial)
+        assert np.isclose(loss, ref, rtol=1e-4)
+        assert np.abs(iso.engine.download_params() - oracle.flatten_params(m)).max() < 1e-5
+
+
+def test_large_batch_split_k_path(pkg, oracle):
+    # B = 4096 exercises the split-K weight-gradient path
+    r = run_pair(pkg, oracle, "c1", N=4096, K=2, minibatch=0, n_iter=1, opt="adam")
+    assert np.allclose(r["loss_lib"], r["loss_ref"], rtol=1e-4)
+    assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=TOL_CHI, atol=TOL_CHI)
+
+
+@pytest.mark.parametrize("kind", ["isa", "pinv"])
+def test_nd_training_iteration(pkg, oracle, kind):
+    r = run_pair(pkg, oracle, "c4", N=512, K=4, minibatch=128, n_iter=2, opt="adam", target=kind)
+    assert np.allclose(r["loss_lib"], r["loss_ref"], rtol=5e-3)
+    assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=1e-3, atol=1e-3)
+
+
+def test_loss_curve_100_iterations(pkg, oracle):
+    # BASELINE config c1: run!(iso, 100) on ADP-shaped data, N=100, K=5, default pairnet + Nesterov
+    r = run_pair(pkg, oracle, "c1", N=100, K=5, minibatch=100, n_iter=100)
+    rel = np.abs(r["loss_lib"] - r["loss_ref"]) / np.abs(r["loss_ref"])
+    assert rel.max() < 1e-2, rel.max()
+    assert rel[:10].max() < 1e-3
+    r = run_pair(pkg, oracle, "c1", N=100, K=5, minibatch=100, n_iter=100, opt="adam")
+    rel = np.abs(r["loss_lib"] - r["loss_ref"]) / np.abs(r["loss_ref"])
+    assert rel[:10].max() < 1e-3 and np.median(rel) < 1e-2
+
+
+def test_nonfinite_loss_raises_domain_error(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    xs, ys = pkg.synthetic.make_data(w, 64, 2)
+    flat = oracle.flatten_params(oracle_model(oracle, w.widths, True, 5))
+    iso = make_iso(pkg, w, xs, ys, flat, minibatch=32)
+    pkg.isotarget(iso)
+    bad = flat.copy()
+    bad[-1] = np.nan                                      # last-layer bias -> NaN outputs
+    iso.engine.upload_params(bad)
+    with pytest.raises(pkg.DomainError) as e:
+        pkg.train_batch_(iso, np.arange(1, 65))
+    assert e.value.code == 2
+    # parameters are left untouched by the failed step (the reference throws before update!)
+    after = iso.engine.download_params()
+    assert np.array_equal(after[:-1], bad[:-1]) and np.isnan(after[-1])
+
+
+def test_params_and_opt_state_roundtrip(pkg, oracle, tmp_path):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    xs, ys = pkg.synthetic.make_data(w, 128, 2)
+    flat = oracle.flatten_params(oracle_model(oracle, w.widths, True, 5))
+    perms = pkg.synthetic.make_perms(w, 128, 4)
+    a = make_iso(pkg, w, xs, ys, flat, opt="adam", minibatch=32)
+    pkg.run_(a, 2, perms=perms[:2])
+    pkg.save(str(tmp_path / "iso.npz"), a)
+    b = make_iso(pkg, w, xs, ys, flat, opt="adam", minibatch=32)
+    pkg.load_state(str(tmp_path / "iso.npz"), b)
+    pkg.run_(a, 2, perms=perms[2:])
+    pkg.run_(b, 2, perms=perms[2:])
+    assert a.losses == b.losses
+    assert np.array_equal(a.engine.download_params(), b.engine.download_params())
+    assert np.array_equal(pkg.cpu(a).model.flat(), a.engine.download_params())
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE-size properties (no oracle at this size: size-independent invariants)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_c3_iteration_properties(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c3"]
+    N, K = w.N, w.K
+    xs, ys = pkg.synthetic.make_data(w)
+    flat = oracle.flatten_params(oracle_model(oracle, w.widths, True, w.seed + 1))
+    iso = make_iso(pkg, w, xs, ys, flat, minibatch=1000)
+    k = pkg.koopman(iso)
+    t = pkg.isotarget(iso)
+    assert t.min() == 0.0 and t.max() == 1.0
+    # shiftscale is the affine map of K-chi fixed by its extrema
+    assert np.allclose(t, (k - k.min()) / (k.max() - k.min()), atol=1e-6)
+    # the K-mean of a sub-sample equals the oracle's on the same rows
+    xsf, ysf = oracle_features(oracle, w, xs[:, :512], ys[:, :, :512])
+    om = oracle.unflatten_params(oracle.Model(list(w.widths), True), flat)
+    assert np.allclose(records(k)[:512], oracle.expectation(om, ysf), rtol=TOL_CHI, atol=1e-5)
+    perms = pkg.synthetic.make_perms(w, N, 2)
+    pkg.run_(iso, 2, perms=perms)
+    assert len(iso.losses) == 2 and np.isfinite(iso.losses).all()
+    assert iso.losses[1] < iso.losses[0] * 1.5
+    st = iso.engine.stats()
+    assert st["kernel_launches"] > 2 * (N // 1000) * 8
