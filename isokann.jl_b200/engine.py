@@ -146,7 +146,9 @@ class Engine:
         self.N, self.K = N, K
 
     def set_koopman_weights(self, w):
-        self._check(self.lib.isokann_set_koopman_weights(self.h, None if w is None else L.ptr(julia_f32(w))))
+        """w: Julia-shaped (K, N_local) weights of WeightedSamples, or None"""
+        buf = None if w is None else julia_f32(w)      # keep the converted buffer alive across the call
+        self._check(self.lib.isokann_set_koopman_weights(self.h, L.ptr(buf)))
 
     # -- parameters --
     def upload_params(self, flat: np.ndarray):
