@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "tc.cuh"
 
 using namespace ik;
 
@@ -138,8 +139,14 @@ void ensure_folded(Ctx &c) {
 
 // featurize (+ parameter-free LayerNorm) M records and run all Dense layers; results stay in
 // c.act[0..L] (row-major M x width).  `in` holds coordinate records (in_is_coords) or features.
+void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords);
+
 void forward_rows(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords) {
   if (M <= 0) return;
+  if (c.tc) {
+    forward_rows_tc(c, in, gather, goff, M, in_is_coords);
+    return;
+  }
   ensure_act(c, M);
   ensure_folded(c);
   const bool pairs = in_is_coords && c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
@@ -155,6 +162,129 @@ void forward_rows(Ctx &c, const float *in, const int64_t *gather, int64_t goff, 
     p.act = (l < c.L - 1) ? c.cfg.activation : c.cfg.last_activation;
     p.epi = EPI_ACT;
     launch_gemm(c, p, true, true, 1);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// tensor-core path (wide nets): split-bf16 activations, tcgen05 GEMMs for layers 0..L-2, thin
+// kernels for the last layer
+// ------------------------------------------------------------------------------------------
+bool tc_eligible(const isokann_config &g) {
+  if (g.n_layers < 2) return false;
+  if (g.widths[0] < 64 || g.widths[g.n_layers] > kMaxD) return false;
+  for (int l = 1; l < g.n_layers; ++l)
+    if (g.widths[l] < 256) return false;
+  return true;
+}
+
+void tc_ensure_rows(Ctx &c, int64_t rows) {
+  TcState &t = *c.tcs;
+  if (rows > t.rows) {
+    for (int l = 0; l < c.L; ++l) t.act[l].ensure(rows, t.wp[l]);
+    c.act[c.L].ensure((size_t)rows * c.d);
+    t.rows = rows;
+  }
+}
+
+void ensure_tc_weights(Ctx &c) {
+  if (c.tc_weights_valid) return;
+  ensure_folded(c);
+  TcState &t = *c.tcs;
+  for (int l = 0; l + 1 < c.L; ++l) {
+    const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
+    t.wF[l].ensure(fout, t.wp[l]);
+    if (l > 0) t.wD[l].ensure(fin, t.wp[l + 1]);
+    launch_prep_weights(c, layer_segment(c, l), fin, fout, t.wF[l].hi.p, t.wF[l].lo.p, t.wp[l],
+                        l > 0 ? t.wD[l].hi.p : nullptr, l > 0 ? t.wD[l].lo.p : nullptr, l > 0 ? t.wp[l + 1] : 0);
+  }
+  c.tc_weights_valid = true;
+}
+
+void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords) {
+  TcState &t = *c.tcs;
+  tc_ensure_rows(c, M);
+  ensure_tc_weights(c);
+  const bool pairs = in_is_coords && c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
+  launch_featurize_split(c, in, gather, goff, M, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0]);
+  for (int l = 0; l + 1 < c.L; ++l) {
+    const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
+    TcGemm g{};
+    g.a_hi = t.act[l].hi.p; g.a_lo = t.act[l].lo.p; g.lda = t.wp[l];
+    g.b_hi = t.wF[l].hi.p; g.b_lo = t.wF[l].lo.p; g.ldb = t.wp[l];
+    g.M = (int)M; g.N = fout; g.K = fin;
+    g.epi = TC_EPI_BIAS_ACT_SPLIT; g.act = c.cfg.activation;
+    g.bias = layer_segment(c, l) + (int64_t)fin * fout;
+    g.out_hi = t.act[l + 1].hi.p; g.out_lo = t.act[l + 1].lo.p; g.ldo = t.wp[l + 1];
+    g.splits = 1;
+    launch_tc_gemm(c, g);
+  }
+  const int l = c.L - 1;
+  launch_thin_forward(c, t.act[l].hi.p, t.act[l].lo.p, M, c.cfg.widths[l], t.wp[l], c.params.p + c.off_w[l], c.d,
+                      c.cfg.last_activation, c.act[c.L].p);
+}
+
+// backward + gradient assembly of one minibatch slice on the tensor-core path; forward_rows_tc and
+// launch_loss_delta (delta of the last layer in c.delta_a, B x d fp32) have already run
+void backward_tc(Ctx &c, int64_t Bloc) {
+  TcState &t = *c.tcs;
+  const int L = c.L, d = c.d;
+  const int64_t ldT = (Bloc + 7) & ~(int64_t)7;
+  int wmax = 0;
+  for (int l = 0; l < L; ++l) wmax = std::max(wmax, c.cfg.widths[l]);
+  t.actT.ensure(wmax + 1, ldT);
+  t.deltaT.ensure(wmax, ldT);
+  int wpmax = 0;
+  for (int l = 0; l < L; ++l) wpmax = std::max(wpmax, t.wp[l]);
+  t.delta[0].ensure(Bloc, wpmax);
+  t.delta[1].ensure(Bloc, wpmax);
+  int cur = 0;
+  {  // last (thin) layer
+    const int l = L - 1, fin = c.cfg.widths[l];
+    launch_transpose_split(c, t.act[l].hi.p, t.act[l].lo.p, Bloc, fin, t.wp[l], t.actT.hi.p, t.actT.lo.p, ldT, true);
+    launch_thin_wgrad(c, t.actT.hi.p, t.actT.lo.p, ldT, fin, Bloc, c.delta_a.p, d, c.grads.p + c.off_w[l]);
+    launch_thin_dgrad(c, c.delta_a.p, Bloc, d, c.params.p + c.off_w[l], fin, t.act[l].hi.p, t.act[l].lo.p, t.wp[l],
+                      c.cfg.activation, t.delta[cur].hi.p, t.delta[cur].lo.p, t.wp[l]);
+  }
+  for (int l = L - 2; l >= 0; --l) {
+    const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
+    // weight + bias gradient: [(fin+1) x fout] = [act_l, 1]^T * delta_{l+1}
+    launch_transpose_split(c, t.act[l].hi.p, t.act[l].lo.p, Bloc, fin, t.wp[l], t.actT.hi.p, t.actT.lo.p, ldT, true);
+    launch_transpose_split(c, t.delta[cur].hi.p, t.delta[cur].lo.p, Bloc, fout, t.wp[l + 1], t.deltaT.hi.p,
+                           t.deltaT.lo.p, ldT, false);
+    float *dest = (l == 0 && c.ln) ? c.gfold.p : c.grads.p + c.off_w[l];
+    TcGemm w{};
+    w.a_hi = t.actT.hi.p; w.a_lo = t.actT.lo.p; w.lda = ldT;
+    w.b_hi = t.deltaT.hi.p; w.b_lo = t.deltaT.lo.p; w.ldb = ldT;
+    w.M = fin + 1; w.N = fout; w.K = (int)Bloc;
+    w.epi = TC_EPI_F32; w.act = ISOKANN_ACT_IDENTITY;
+    w.ldc = fout;
+    const int tiles = cdiv(w.M, 128) * cdiv(w.N, 256);
+    int splits = std::max(1, std::min((c.num_sms + tiles / 2) / tiles, (int)(Bloc / 2048)));
+    if (splits > 1) {
+      c.splitk.ensure((size_t)splits * w.M * w.N);
+      w.out_f32 = c.splitk.p;
+      w.splits = splits;
+      const int used = launch_tc_gemm(c, w);
+      launch_splitk_reduce(c, c.splitk.p, used, (int64_t)w.M * w.N, dest);
+    } else {
+      w.out_f32 = dest;
+      w.splits = 1;
+      launch_tc_gemm(c, w);
+    }
+    if (l > 0) {
+      // delta_l = (delta_{l+1} * W_l^T) .* act'(z_l)
+      TcGemm g{};
+      g.a_hi = t.delta[cur].hi.p; g.a_lo = t.delta[cur].lo.p; g.lda = t.wp[l + 1];
+      g.b_hi = t.wD[l].hi.p; g.b_lo = t.wD[l].lo.p; g.ldb = t.wp[l + 1];
+      g.M = (int)Bloc; g.N = fin; g.K = fout;
+      g.epi = TC_EPI_MULDACT_SPLIT; g.act = c.cfg.activation;
+      g.z_hi = t.act[l].hi.p; g.z_lo = t.act[l].lo.p; g.ldz = t.wp[l];
+      g.out_hi = t.delta[cur ^ 1].hi.p; g.out_lo = t.delta[cur ^ 1].lo.p; g.ldo = t.wp[l];
+      g.splits = 1;
+      launch_tc_gemm(c, g);
+      cur ^= 1;
+    }
   }
 }
 
@@ -504,7 +634,8 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
     float *cur = c.delta_a.p, *other = c.delta_b.p;
     launch_loss_delta(c, c.act[L].p, c.target.p, c.perm_dev.p, s0, c.w_loss.p, Bloc, d, (double)len,
                       c.cfg.last_activation, cur, c.red_d.p, c.ticket.p, c.grads.p + c.P);
-    for (int l = L - 1; l >= 0; --l) {
+    if (c.tc) backward_tc(c, Bloc);
+    for (int l = L - 1; l >= 0 && !c.tc; --l) {
       const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
       // weight + bias gradient: [(fin+1) x fout] = [act[l], 1]^T * delta
       float *dest = (l == 0 && c.ln) ? c.gfold.p : c.grads.p + c.off_w[l];
@@ -556,6 +687,7 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
     c.beta_t[1] *= c.cfg.beta2;
   }
   c.folded_valid = false;
+  c.tc_weights_valid = false;
 }
 
 double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool partial) {
@@ -754,6 +886,17 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
       c->folded1.ensure(seg);
       c->gfold.ensure(seg);
     }
+    if (cfg->gemm_mode == ISOKANN_GEMM_TC)
+      IK_REQUIRE(tc_eligible(*cfg), ISOKANN_BAD_ARGUMENT,
+                 "ISOKANN_GEMM_TC needs >= 2 layers, hidden widths >= 256, input width >= 64, output <= 8");
+    c->tc = cfg->gemm_mode != ISOKANN_GEMM_FP32 && tc_eligible(*cfg);
+    if (c->tc) {
+      c->tcs = new TcState;
+      c->tcs->act.resize(c->L);
+      c->tcs->wF.resize(c->L);
+      c->tcs->wD.resize(c->L);
+      for (int l = 0; l <= c->L; ++l) c->tcs->wp.push_back((cfg->widths[l] + 63) & ~63);
+    }
     c->beta_t[0] = cfg->beta1;
     c->beta_t[1] = cfg->beta2;
     c->act.resize(c->L + 1);
@@ -790,6 +933,16 @@ int32_t isokann_destroy(isokann_ctx *c) {
                          &c->kweights, &c->chi_x, &c->kchi, &c->kchi_loc, &c->gather_pad, &c->target, &c->w_loss,
                          &c->delta_a, &c->delta_b, &c->splitk, &c->staging_in, &c->staging_out, &c->red_f};
   for (auto *b : fb) b->release();
+  if (c->tcs) {
+    for (auto &b : c->tcs->act) b.release();
+    for (auto &b : c->tcs->wF) b.release();
+    for (auto &b : c->tcs->wD) b.release();
+    c->tcs->actT.release();
+    c->tcs->deltaT.release();
+    c->tcs->delta[0].release();
+    c->tcs->delta[1].release();
+    delete c->tcs;
+  }
   c->pairs.release();
   c->red_d.release();
   c->epoch_loss.release();
@@ -886,6 +1039,7 @@ int32_t isokann_upload_params(isokann_ctx *c, const float *flat, int64_t P) {
     IK_CUDA(cudaMemcpyAsync(c->params.p, flat, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     sync_stream(*c);
     c->folded_valid = false;
+    c->tc_weights_valid = false;
   });
 }
 

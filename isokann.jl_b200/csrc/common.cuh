@@ -154,6 +154,8 @@ int nccl_allreduce_sum_f32(Nccl *n, void *comm, float *buf, size_t count, cudaSt
 int nccl_allgather_f32(Nccl *n, void *comm, const float *send, float *recv, size_t count_per_rank, cudaStream_t s,
                        std::string &err);
 
+struct TcState;  // tensor-core path buffers (tc.cuh)
+
 struct Ctx {
   isokann_config cfg{};
   std::vector<int32_t> index;
@@ -170,6 +172,9 @@ struct Ctx {
   DevBuf<float> params, grads, opt_m, opt_v, folded1, gfold;
   float beta_t[2] = {0.f, 0.f};
   bool folded_valid = false;  // folded1 matches the current parameters
+  bool tc = false;            // wide Dense layers run on tcgen05 (3xBF16 split)
+  bool tc_weights_valid = false;
+  TcState *tcs = nullptr;
   DevBuf<int2> pairs;  // coordinate offsets (3a, 3b) per feature
   int n_pairs = 0;
 

@@ -10,6 +10,7 @@
 //
 // Algorithmic HBM traffic per record: 4*D read + 4*F written.
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace ik {
 
@@ -24,7 +25,8 @@ __global__ void __launch_bounds__(256) featurize_ln_kernel(const float *__restri
                                                            const int64_t *__restrict__ gather, int64_t M, int D,
                                                            int F, const int2 *__restrict__ pairs, int do_ln,
                                                            float eps2, float *__restrict__ out, int64_t ldo,
-                                                           int Dp, int Fp) {
+                                                           int Dp, int Fp, __nv_bfloat16 *__restrict__ out_hi,
+                                                           __nv_bfloat16 *__restrict__ out_lo) {
   extern __shared__ float sm[];
   const int warps = blockDim.x >> 5;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -53,26 +55,36 @@ __global__ void __launch_bounds__(256) featurize_ln_kernel(const float *__restri
         s += v;
       }
     }
-    float *o = out + m * ldo;
+    float mu = 0.f, rstd = 1.f;
     if (do_ln) {
-      const float mu = warp_sum(s) / (float)F;
+      mu = warp_sum(s) / (float)F;
       float q = 0.f;
       for (int f = lane; f < F; f += 32) {
         const float t = sf[f] - mu;
         q = fmaf(t, t, q);
       }
       const float var = warp_sum(q) / (float)F;
-      const float rstd = 1.0f / sqrtf(var + eps2);
-      for (int f = lane; f < F; f += 32) o[f] = (sf[f] - mu) * rstd;
+      rstd = 1.0f / sqrtf(var + eps2);
+    }
+    if (out_hi) {  // bf16 (hi, lo) split for the tensor-core path; pad columns [F, ldo) are zeroed
+      __nv_bfloat16 *oh = out_hi + m * ldo, *ol = out_lo + m * ldo;
+      for (int f = lane; f < (int)ldo; f += 32) {
+        const float v = f < F ? (sf[f] - mu) * rstd : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        oh[f] = h;
+        ol[f] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
     } else {
-      for (int f = lane; f < F; f += 32) o[f] = sf[f];
+      float *o = out + m * ldo;
+      for (int f = lane; f < F; f += 32) o[f] = (sf[f] - mu) * rstd;
     }
     __syncwarp();
   }
 }
 
-void launch_featurize(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M, bool pairs,
-                      bool do_ln, float *out, int64_t ldo) {
+static void launch_featurize_impl(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M,
+                                  bool pairs, bool do_ln, float *out, int64_t ldo, __nv_bfloat16 *out_hi,
+                                  __nv_bfloat16 *out_lo) {
   if (M <= 0) return;
   const int D = pairs ? c.D : c.F;  // identity featurizer: records are already features
   const int F = c.F;
@@ -96,10 +108,20 @@ void launch_featurize(Ctx &c, const float *coords, const int64_t *gather, int64_
   c.timer.begin(KC_FEATURIZE, c.stream);
   featurize_ln_kernel<<<grid, warps * 32, smem, c.stream>>>(coords, gather ? gather + gather_off : nullptr, M, D, F,
                                                             pairs ? c.pairs.p : nullptr, do_ln ? 1 : 0, eps * eps,
-                                                            out, ldo, Dp, Fp);
+                                                            out, ldo, Dp, Fp, out_hi, out_lo);
   c.timer.end(c.stream);
   IK_CUDA(cudaGetLastError());
   c.count_launch(KC_FEATURIZE, 4.0 * (double)(D + F) * (double)M);
+}
+
+void launch_featurize(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M, bool pairs,
+                      bool do_ln, float *out, int64_t ldo) {
+  launch_featurize_impl(c, coords, gather, gather_off, M, pairs, do_ln, out, ldo, nullptr, nullptr);
+}
+
+void launch_featurize_split(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M,
+                            bool pairs, bool do_ln, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld) {
+  launch_featurize_impl(c, coords, gather, gather_off, M, pairs, do_ln, nullptr, ld, out_hi, out_lo);
 }
 
 }  // namespace ik

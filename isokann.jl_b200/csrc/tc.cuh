@@ -1,0 +1,81 @@
+// Tensor-core (tcgen05) path: split-bf16 operand buffers and the kernels around the GEMM.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ik {
+
+enum { TC_EPI_BIAS_ACT_SPLIT = 0, TC_EPI_F32 = 1, TC_EPI_MULDACT_SPLIT = 2 };
+
+// D[M x N] = A[M x K] * B[N x K]^T with A, B given as bf16 (hi, lo) pairs, K contiguous
+struct TcGemm {
+  const __nv_bfloat16 *a_hi, *a_lo;
+  int64_t lda;
+  const __nv_bfloat16 *b_hi, *b_lo;
+  int64_t ldb;
+  int M, N, K;
+  int epi, act;
+  const float *bias;                  // TC_EPI_BIAS_ACT_SPLIT
+  __nv_bfloat16 *out_hi, *out_lo;     // split outputs
+  int64_t ldo;
+  float *out_f32;                     // TC_EPI_F32 (split-K slice s at out_f32 + s*M*ldc)
+  int64_t ldc;
+  const __nv_bfloat16 *z_hi, *z_lo;   // TC_EPI_MULDACT_SPLIT
+  int64_t ldz;
+  int splits;
+};
+
+int launch_tc_gemm(Ctx &c, const TcGemm &g);  // returns the number of split-K slices written
+
+// a split-bf16 matrix: hi/lo planes, rows x ld
+struct SplitBuf {
+  DevBuf<__nv_bfloat16> hi, lo;
+  int64_t rows = 0, ld = 0;
+  void ensure(int64_t r, int64_t l) {
+    if (r * l > (int64_t)hi.n) {
+      hi.ensure((size_t)(r * l));
+      lo.ensure((size_t)(r * l));
+    }
+    rows = r;
+    ld = l;
+  }
+  void release() {
+    hi.release();
+    lo.release();
+  }
+};
+
+struct TcState {
+  std::vector<SplitBuf> act;   // act[l], l = 0..L-1: row-major rows x wp_l
+  std::vector<SplitBuf> wF;    // forward operand of layer l (l = 0..L-2): [w_{l+1} x wp_l]
+  std::vector<SplitBuf> wD;    // dgrad operand of layer l   (l = 1..L-2): [w_l x wp_{l+1}]
+  SplitBuf actT, deltaT;       // transposed activation (+ ones row) / delta of the current layer
+  SplitBuf delta[2];           // row-major delta ping-pong
+  std::vector<int> wp;         // padded widths
+  int64_t rows = 0, train_rows = 0;
+};
+
+// featurizer + LayerNorm writing the split-bf16 A operand [M x ld] (pad columns zeroed)
+void launch_featurize_split(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M,
+                            bool pairs, bool do_ln, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld);
+// [rows x cols] split (ld_in) -> transposed [cols(+ones row) x ld_out] split; columns >= rows are zero
+void launch_transpose_split(Ctx &c, const __nv_bfloat16 *in_hi, const __nv_bfloat16 *in_lo, int64_t rows, int cols,
+                            int64_t ld_in, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld_out,
+                            bool ones_row);
+// weights of one Dense layer: flat fp32 segment seg[(in) x out] (row-major) ->
+//   fwd operand  Wf[out x ld_f] (K = in contiguous) and dgrad operand Wd[in x ld_d] (K = out contiguous)
+void launch_prep_weights(Ctx &c, const float *seg, int fin, int fout, __nv_bfloat16 *wf_hi, __nv_bfloat16 *wf_lo,
+                         int64_t ld_f, __nv_bfloat16 *wd_hi, __nv_bfloat16 *wd_lo, int64_t ld_d);
+// last (thin) Dense layer from a split activation: chi[m, a] = act(sum_k z[m,k] W[k,a] + b[a])
+void launch_thin_forward(Ctx &c, const __nv_bfloat16 *z_hi, const __nv_bfloat16 *z_lo, int64_t M, int fin, int64_t ldz,
+                         const float *seg, int d, int act, float *chi);
+// delta_prev[m,k] = (sum_a delta[m,a] W[k,a]) * act'(z[m,k]) written split (row-major)
+void launch_thin_dgrad(Ctx &c, const float *delta, int64_t M, int d, const float *seg, int fin,
+                       const __nv_bfloat16 *z_hi, const __nv_bfloat16 *z_lo, int64_t ldz, int act,
+                       __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ldo);
+// grad[(fin+1) x d] = [z, 1]^T * delta from the transposed split activation zT[(fin+1) x ldt]
+void launch_thin_wgrad(Ctx &c, const __nv_bfloat16 *zt_hi, const __nv_bfloat16 *zt_lo, int64_t ldt, int fin, int64_t M,
+                       const float *delta, int d, float *grad);
+
+}  // namespace ik

@@ -1,0 +1,295 @@
+// Kernels around the tcgen05 GEMM: operand preparation (fp32 -> bf16 hi/lo split, transposes)
+// and the thin last Dense layer (out = d <= 8), which is a memory-bound row reduction rather
+// than a GEMM.  All of them are HBM-bound passes with 16-byte vector accesses.
+#include "tc.cuh"
+
+namespace ik {
+
+namespace {
+
+__device__ __forceinline__ void split1(float x, __nv_bfloat16 &h, __nv_bfloat16 &l) {
+  h = __float2bfloat16_rn(x);
+  l = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+__device__ __forceinline__ float bflo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bfhi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ float act_f(float a, int kind) {
+  switch (kind) {
+    case ISOKANN_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-a));
+    case ISOKANN_ACT_TANH: return tanhf(a);
+    case ISOKANN_ACT_RELU: return fmaxf(a, 0.f);
+    default: return a;
+  }
+}
+__device__ __forceinline__ float dact_f(float z, int kind) {
+  switch (kind) {
+    case ISOKANN_ACT_SIGMOID: return z * (1.0f - z);
+    case ISOKANN_ACT_TANH: return 1.0f - z * z;
+    case ISOKANN_ACT_RELU: return z > 0.f ? 1.0f : 0.f;
+    default: return 1.0f;
+  }
+}
+
+// ---- 64x64 tile transpose of a split matrix ----
+__global__ void __launch_bounds__(256) transpose_split_kernel(const __nv_bfloat16 *__restrict__ in_hi,
+                                                              const __nv_bfloat16 *__restrict__ in_lo, int64_t rows,
+                                                              int cols, int64_t ld_in,
+                                                              __nv_bfloat16 *__restrict__ out_hi,
+                                                              __nv_bfloat16 *__restrict__ out_lo, int64_t ld_out,
+                                                              int ones_row) {
+  __shared__ __nv_bfloat16 th[64][66], tl[64][66];
+  const int64_t r0 = (int64_t)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  for (int i = ty; i < 64; i += 4) {
+    const int64_t r = r0 + i;
+    const int cc = c0 + tx;
+    __nv_bfloat16 h = __float2bfloat16_rn(0.f), l = h;
+    if (r < rows && cc < cols) {
+      h = in_hi[r * ld_in + cc];
+      l = in_lo[r * ld_in + cc];
+    }
+    th[i][tx] = h;
+    tl[i][tx] = l;
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 4) {
+    const int cc = c0 + i;       // output row
+    const int64_t r = r0 + tx;   // output column
+    if (cc < cols && r < rows) {
+      out_hi[(int64_t)cc * ld_out + r] = th[tx][i];
+      out_lo[(int64_t)cc * ld_out + r] = tl[tx][i];
+    }
+  }
+  if (ones_row && blockIdx.y == 0) {
+    for (int i = threadIdx.x; i < 64; i += 256) {
+      const int64_t r = r0 + i;
+      if (r < rows) {
+        out_hi[(int64_t)cols * ld_out + r] = __float2bfloat16_rn(1.0f);
+        out_lo[(int64_t)cols * ld_out + r] = __float2bfloat16_rn(0.0f);
+      }
+    }
+  }
+}
+
+// ---- weights: fp32 [fin x fout] -> Wd split (same orientation) and Wf split (transposed) ----
+__global__ void __launch_bounds__(256) prep_weights_kernel(const float *__restrict__ seg, int fin, int fout,
+                                                           __nv_bfloat16 *__restrict__ wf_hi,
+                                                           __nv_bfloat16 *__restrict__ wf_lo, int64_t ld_f,
+                                                           __nv_bfloat16 *__restrict__ wd_hi,
+                                                           __nv_bfloat16 *__restrict__ wd_lo, int64_t ld_d) {
+  __shared__ float t[64][65];
+  const int i0 = blockIdx.x * 64;  // fin index
+  const int j0 = blockIdx.y * 64;  // fout index
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int r = ty; r < 64; r += 4) {
+    const int i = i0 + r, j = j0 + tx;
+    float v = 0.f;
+    if (i < fin && j < fout) {
+      v = seg[(int64_t)i * fout + j];
+      if (wd_hi) {
+        __nv_bfloat16 h, l;
+        split1(v, h, l);
+        wd_hi[(int64_t)i * ld_d + j] = h;
+        wd_lo[(int64_t)i * ld_d + j] = l;
+      }
+    }
+    t[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 64; r += 4) {
+    const int j = j0 + r, i = i0 + tx;
+    if (j < fout && i < fin) {
+      __nv_bfloat16 h, l;
+      split1(t[tx][r], h, l);
+      wf_hi[(int64_t)j * ld_f + i] = h;
+      wf_lo[(int64_t)j * ld_f + i] = l;
+    }
+  }
+}
+
+// ---- thin forward: one warp per row ----
+__global__ void __launch_bounds__(256) thin_forward_kernel(const __nv_bfloat16 *__restrict__ z_hi,
+                                                           const __nv_bfloat16 *__restrict__ z_lo, int64_t M, int fin,
+                                                           int64_t ldz, const float *__restrict__ seg, int d, int act,
+                                                           float *__restrict__ chi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t m = wid; m < M; m += nw) {
+    float acc[kMaxD];
+#pragma unroll
+    for (int a = 0; a < kMaxD; ++a) acc[a] = 0.f;
+    const uint4 *ph = reinterpret_cast<const uint4 *>(z_hi + m * ldz);
+    const uint4 *pl = reinterpret_cast<const uint4 *>(z_lo + m * ldz);
+    for (int k8 = lane; k8 * 8 < fin; k8 += 32) {
+      const uint4 h = __ldg(ph + k8), l = __ldg(pl + k8);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k8 * 8 + 2 * e;
+        const float z0 = bflo(hw[e]) + bflo(lw[e]);
+        const float z1 = bfhi(hw[e]) + bfhi(lw[e]);
+#pragma unroll
+        for (int a = 0; a < kMaxD; ++a) {
+          if (a < d) {
+            if (k < fin) acc[a] = fmaf(z0, __ldg(seg + (int64_t)k * d + a), acc[a]);
+            if (k + 1 < fin) acc[a] = fmaf(z1, __ldg(seg + (int64_t)(k + 1) * d + a), acc[a]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < kMaxD; ++a) {
+      if (a < d) {
+        float s = acc[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) chi[m * d + a] = act_f(s + __ldg(seg + (int64_t)fin * d + a), act);
+      }
+    }
+  }
+}
+
+// ---- thin dgrad: 8 consecutive k per thread ----
+__global__ void __launch_bounds__(256) thin_dgrad_kernel(const float *__restrict__ delta, int64_t M, int d,
+                                                         const float *__restrict__ seg, int fin,
+                                                         const __nv_bfloat16 *__restrict__ z_hi,
+                                                         const __nv_bfloat16 *__restrict__ z_lo, int64_t ldz, int act,
+                                                         __nv_bfloat16 *__restrict__ out_hi,
+                                                         __nv_bfloat16 *__restrict__ out_lo, int64_t ldo) {
+  const int k8n = (int)(ldo / 8);
+  const int64_t total = M * k8n;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / k8n;
+    const int k0 = (int)(t - m * k8n) * 8;
+    float dl[kMaxD];
+#pragma unroll
+    for (int a = 0; a < kMaxD; ++a) dl[a] = a < d ? __ldg(delta + m * d + a) : 0.f;
+    uint4 h = make_uint4(0, 0, 0, 0), l = h;
+    if (k0 < ldz) {
+      h = __ldg(reinterpret_cast<const uint4 *>(z_hi + m * ldz + k0));
+      l = __ldg(reinterpret_cast<const uint4 *>(z_lo + m * ldz + k0));
+    }
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float g[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int k = k0 + 2 * e + q;
+        float s = 0.f;
+        if (k < fin) {
+#pragma unroll
+          for (int a = 0; a < kMaxD; ++a)
+            if (a < d) s = fmaf(dl[a], __ldg(seg + (int64_t)k * d + a), s);
+          const float z = q == 0 ? bflo(hw[e]) + bflo(lw[e]) : bfhi(hw[e]) + bfhi(lw[e]);
+          s *= dact_f(z, act);
+        }
+        g[q] = s;
+      }
+      __nv_bfloat16 h0, l0, h1, l1;
+      split1(g[0], h0, l0);
+      split1(g[1], h1, l1);
+      oh[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      ol[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4 *>(out_hi + m * ldo + k0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4 *>(out_lo + m * ldo + k0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  }
+}
+
+// ---- thin wgrad: one block per row k of zT (row fin = ones -> bias gradient) ----
+__global__ void __launch_bounds__(256) thin_wgrad_kernel(const __nv_bfloat16 *__restrict__ zt_hi,
+                                                         const __nv_bfloat16 *__restrict__ zt_lo, int64_t ldt,
+                                                         int64_t M, const float *__restrict__ delta, int d,
+                                                         float *__restrict__ grad) {
+  __shared__ float sh[8][kMaxD];
+  const int k = blockIdx.x;
+  float acc[kMaxD];
+#pragma unroll
+  for (int a = 0; a < kMaxD; ++a) acc[a] = 0.f;
+  const __nv_bfloat16 *ph = zt_hi + (int64_t)k * ldt, *pl = zt_lo + (int64_t)k * ldt;
+  for (int64_t m = threadIdx.x; m < M; m += blockDim.x) {
+    const float z = __bfloat162float(ph[m]) + __bfloat162float(pl[m]);
+#pragma unroll
+    for (int a = 0; a < kMaxD; ++a)
+      if (a < d) acc[a] = fmaf(z, __ldg(delta + m * d + a), acc[a]);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < kMaxD; ++a) {
+    float s = acc[a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sh[w][a] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < d) {
+    float s = 0.f;
+    for (int ww = 0; ww < 8; ++ww) s += sh[ww][threadIdx.x];
+    grad[(int64_t)k * d + threadIdx.x] = s;
+  }
+}
+
+}  // namespace
+
+void launch_transpose_split(Ctx &c, const __nv_bfloat16 *in_hi, const __nv_bfloat16 *in_lo, int64_t rows, int cols,
+                            int64_t ld_in, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld_out,
+                            bool ones_row) {
+  if (rows <= 0) return;
+  dim3 grid(cdiv(rows, 64), cdiv(cols, 64));
+  c.timer.begin(KC_TRAIN_EW, c.stream);
+  transpose_split_kernel<<<grid, 256, 0, c.stream>>>(in_hi, in_lo, rows, cols, ld_in, out_hi, out_lo, ld_out,
+                                                     ones_row ? 1 : 0);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_TRAIN_EW);
+}
+
+void launch_prep_weights(Ctx &c, const float *seg, int fin, int fout, __nv_bfloat16 *wf_hi, __nv_bfloat16 *wf_lo,
+                         int64_t ld_f, __nv_bfloat16 *wd_hi, __nv_bfloat16 *wd_lo, int64_t ld_d) {
+  dim3 grid(cdiv(fin, 64), cdiv(fout, 64));
+  c.timer.begin(KC_TRAIN_EW, c.stream);
+  prep_weights_kernel<<<grid, 256, 0, c.stream>>>(seg, fin, fout, wf_hi, wf_lo, ld_f, wd_hi, wd_lo, ld_d);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_TRAIN_EW);
+}
+
+void launch_thin_forward(Ctx &c, const __nv_bfloat16 *z_hi, const __nv_bfloat16 *z_lo, int64_t M, int fin, int64_t ldz,
+                         const float *seg, int d, int act, float *chi) {
+  if (M <= 0) return;
+  int64_t want = (M + 7) / 8;
+  int grid = (int)std::min<int64_t>(want, (int64_t)c.num_sms * 8);
+  c.timer.begin(KC_REDUCE, c.stream);
+  thin_forward_kernel<<<grid, 256, 0, c.stream>>>(z_hi, z_lo, M, fin, ldz, seg, d, act, chi);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_REDUCE);
+}
+
+void launch_thin_dgrad(Ctx &c, const float *delta, int64_t M, int d, const float *seg, int fin,
+                       const __nv_bfloat16 *z_hi, const __nv_bfloat16 *z_lo, int64_t ldz, int act,
+                       __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ldo) {
+  if (M <= 0) return;
+  const int64_t total = M * (ldo / 8);
+  int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c.num_sms * 16);
+  c.timer.begin(KC_TRAIN_EW, c.stream);
+  thin_dgrad_kernel<<<grid, 256, 0, c.stream>>>(delta, M, d, seg, fin, z_hi, z_lo, ldz, act, out_hi, out_lo, ldo);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_TRAIN_EW);
+}
+
+void launch_thin_wgrad(Ctx &c, const __nv_bfloat16 *zt_hi, const __nv_bfloat16 *zt_lo, int64_t ldt, int fin, int64_t M,
+                       const float *delta, int d, float *grad) {
+  c.timer.begin(KC_TRAIN_EW, c.stream);
+  thin_wgrad_kernel<<<fin + 1, 256, 0, c.stream>>>(zt_hi, zt_lo, ldt, M, delta, d, grad);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_TRAIN_EW);
+}
+
+}  // namespace ik

@@ -1,0 +1,419 @@
+// tcgen05 / TMA GEMM for the wide Dense layers (fp32-accurate 3xBF16 split).
+//
+// Replaces the cuBLAS SGEMM + broadcast kernels behind Flux.Dense forward/backward for wide
+// layers (reference call sites src/isotarget.jl:18, src/iso.jl:185).  The reference computes in
+// FP32; tensor cores are reached without giving that up by splitting every operand into two
+// bf16 terms  x = hi + lo  (hi = bf16(x), lo = bf16(x - hi), 16 mantissa bits kept) and issuing
+// three MMAs per k-slice into one fp32 TMEM accumulator:  hi*hi + hi*lo + lo*hi  (the dropped
+// lo*lo term is ~2^-16 relative).
+//
+//   D[M x N] = A[M x K] * B[N x K]^T            A, B: K-major bf16 (hi, lo), fp32 accumulate
+//
+// Structure (one CTA per SM, persistent over output tiles of 128 x 256):
+//   warp 0   : TMA producer  - 4 tiles per stage (A_hi, A_lo, B_hi, B_lo), 128B swizzle, 2 stages
+//   warp 1   : MMA issuer    - one elected lane issues tcgen05.mma (M=128, N=256, K=16) x 3 x 4 per
+//              stage; tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2-5: epilogue      - tcgen05.ld the fp32 accumulator (double-buffered in TMEM: 2 x 256
+//              columns, so the epilogue of tile i overlaps the MMAs of tile i+1), fuse
+//              bias + activation (or the activation derivative of the backward pass), split to
+//              bf16 hi/lo for the next layer's A operand, or store fp32 (weight gradients).
+// Out-of-range rows/columns/k are zero-filled by TMA; stores are predicated.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace ik {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 2;
+constexpr int A_TILE = BM * BK * 2;  // bytes of one bf16 A tile
+constexpr int B_TILE = BN * BK * 2;
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // 96 KiB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NTHREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded spin: a protocol bug must surface as a trap, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float act_fwd(float a, int kind) {
+  switch (kind) {
+    case ISOKANN_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-a));
+    case ISOKANN_ACT_TANH: return tanhf(a);
+    case ISOKANN_ACT_RELU: return fmaxf(a, 0.f);
+    default: return a;
+  }
+}
+__device__ __forceinline__ float dact_o(float z, int kind) {
+  switch (kind) {
+    case ISOKANN_ACT_SIGMOID: return z * (1.0f - z);
+    case ISOKANN_ACT_TANH: return 1.0f - z * z;
+    case ISOKANN_ACT_RELU: return z > 0.f ? 1.0f : 0.f;
+    default: return 1.0f;
+  }
+}
+
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+  const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+  hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+struct TcParams {
+  int M, N, K;          // D is M x N, reduction length K (elements)
+  int m_tiles, n_tiles, splits, kb_per_split, num_kb;
+  int epi, act;
+  const float *bias;    // [N] or nullptr
+  __nv_bfloat16 *out_hi, *out_lo;  // split outputs, row-major, leading dimension ldo
+  int64_t ldo;
+  float *out_f32;       // fp32 output (+ split-K slices of M*ldc)
+  int64_t ldc;
+  const __nv_bfloat16 *z_hi, *z_lo;  // EPI_MULDACT: activation outputs (split), leading dimension ldz
+  int64_t ldz;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+               const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;            // 1024-B alignment for SWIZZLE_128B
+  uint8_t *base_ptr = smem_raw + (base - raw);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(base_ptr + STAGES * STAGE_BYTES);
+  // barrier slots: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * STAGES;
+  const uint32_t bar_tfull = bar_empty + 8 * STAGES, bar_tempty = bar_tfull + 16;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is a warp-wide operation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / (p.m_tiles * p.n_tiles);
+        const int rem = t - split * (p.m_tiles * p.n_tiles);
+        const int mb = rem / p.n_tiles, nb = rem - mb * p.n_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_arrive_expect_tx(full, STAGE_BYTES);
+          tma_load_2d(sa, &map_ah, full, kb * BK, mb * BM);
+          tma_load_2d(sa + A_TILE, &map_al, full, kb * BK, mb * BM);
+          tma_load_2d(sa + 2 * A_TILE, &map_bh, full, kb * BK, nb * BN);
+          tma_load_2d(sa + 2 * A_TILE + B_TILE, &map_bl, full, kb * BK, nb * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int split = t / (p.m_tiles * p.n_tiles);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * STAGE_BYTES;
+          const uint64_t dah = make_desc_sw128(sa), dal = make_desc_sw128(sa + A_TILE);
+          const uint64_t dbh = make_desc_sw128(sa + 2 * A_TILE), dbl = make_desc_sw128(sa + 2 * A_TILE + B_TILE);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 16 bf16 = 32 B inside the swizzle atom
+            umma_f16(tmem_d, dah + adv, dbh + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_f16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+            umma_f16(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+          }
+          umma_commit(bar_empty + 8 * stage);  // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int split = t / (p.m_tiles * p.n_tiles);
+      const int rem = t - split * (p.m_tiles * p.n_tiles);
+      const int mb = rem / p.n_tiles, nb = rem - mb * p.n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int64_t row = (int64_t)mb * BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        const int col0 = nb * BN + c;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr0 + c, r);
+        if (!row_ok) continue;
+        if (p.epi == TC_EPI_F32) {
+          float *dst = p.out_f32 + (int64_t)split * p.M * p.ldc + row * p.ldc + col0;
+          if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4 *>(dst + j) =
+                  make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                              __uint_as_float(r[j + 3]));
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]);
+          }
+        } else {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.epi == TC_EPI_BIAS_ACT_SPLIT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float b = (p.bias && col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
+              v[j] = act_fwd(v[j] + b, p.act);
+            }
+          } else {  // TC_EPI_MULDACT_SPLIT
+            const uint4 *zh = reinterpret_cast<const uint4 *>(p.z_hi + row * p.ldz + col0);
+            const uint4 *zl = reinterpret_cast<const uint4 *>(p.z_lo + row * p.ldz + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 h = __ldg(zh + q), l = __ldg(zl + q);
+              const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float z0 = bf16lo(hw[e]) + bf16lo(lw[e]);
+                const float z1 = bf16hi(hw[e]) + bf16hi(lw[e]);
+                v[q * 8 + 2 * e] *= dact_o(z0, p.act);
+                v[q * 8 + 2 * e + 1] *= dact_o(z1, p.act);
+              }
+            }
+          }
+          // columns >= N inside the padded leading dimension are written as zeros
+          uint32_t ph[16], pl[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x0 = (col0 + 2 * j < p.N) ? v[2 * j] : 0.f;
+            const float x1 = (col0 + 2 * j + 1 < p.N) ? v[2 * j + 1] : 0.f;
+            split_pair(x0, x1, ph[j], pl[j]);
+          }
+          uint4 *dh = reinterpret_cast<uint4 *>(p.out_hi + row * p.ldo + col0);
+          uint4 *dl = reinterpret_cast<uint4 *>(p.out_lo + row * p.ldo + col0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            dh[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+            dl[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void *sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  IK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+  IK_REQUIRE(sym != nullptr && qres == cudaDriverEntryPointSuccess, ISOKANN_ERR_CUDA,
+             "cuTensorMapEncodeTiled is not available from this driver");
+  fn = (EncodeTiledFn)sym;
+  return fn;
+}
+
+// rows x cols bf16, row-major with leading dimension ld (elements); box = box_rows x 64 columns
+void make_map(CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  IK_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, ISOKANN_BAD_ARGUMENT,
+             "tensor-core operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IK_REQUIRE(r == CUDA_SUCCESS, ISOKANN_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+}
+
+}  // namespace
+
+int launch_tc_gemm(Ctx &c, const TcGemm &g) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+  static bool attr = false;
+  if (!attr) {
+    IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr = true;
+  }
+  alignas(64) CUtensorMap mah, mal, mbh, mbl;
+  make_map(&mah, g.a_hi, g.M, g.K, g.lda, BM);
+  make_map(&mal, g.a_lo, g.M, g.K, g.lda, BM);
+  make_map(&mbh, g.b_hi, g.N, g.K, g.ldb, BN);
+  make_map(&mbl, g.b_lo, g.N, g.K, g.ldb, BN);
+  TcParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.m_tiles = cdiv(g.M, BM);
+  p.n_tiles = cdiv(g.N, BN);
+  p.num_kb = cdiv(g.K, BK);
+  int splits = g.splits < 1 ? 1 : g.splits;
+  if (g.epi != TC_EPI_F32) splits = 1;
+  splits = std::min(splits, p.num_kb);
+  p.kb_per_split = cdiv(p.num_kb, splits);
+  p.splits = cdiv(p.num_kb, p.kb_per_split);
+  p.epi = g.epi; p.act = g.act;
+  p.bias = g.bias;
+  p.out_hi = g.out_hi; p.out_lo = g.out_lo; p.ldo = g.ldo;
+  p.out_f32 = g.out_f32; p.ldc = g.ldc;
+  p.z_hi = g.z_hi; p.z_lo = g.z_lo; p.ldz = g.ldz;
+  if (g.epi != TC_EPI_F32)
+    IK_REQUIRE(g.ldo % 8 == 0 && g.ldo >= (int64_t)p.n_tiles * 0 + ((g.N + 31) / 32) * 32, ISOKANN_BAD_ARGUMENT,
+               "split output needs a leading dimension padded to 32 columns");
+  if (g.epi == TC_EPI_MULDACT_SPLIT)
+    IK_REQUIRE(g.ldz % 8 == 0 && g.ldz >= ((g.N + 31) / 32) * 32, ISOKANN_BAD_ARGUMENT, "z leading dimension");
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = std::min(total, c.num_sms);
+  c.timer.begin(KC_GEMM, c.stream);
+  tc_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_GEMM, 2.0 * (double)g.M * (double)g.N * (double)g.K);
+  return p.splits;
+}
+
+}  // namespace ik

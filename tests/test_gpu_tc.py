@@ -1,0 +1,93 @@
+"""Parity of the tcgen05 (3xBF16 split) path for wide Dense layers against the oracle and
+against the library's own FP32 CUDA-core path, through the C ABI."""
+import copy
+
+import numpy as np
+import pytest
+
+from tests.helpers import make_iso, oracle_features, oracle_model, records, run_pair
+
+pytestmark = pytest.mark.gpu
+
+TOL_CHI = 1e-4
+
+
+def wide(pkg, widths, name="c1"):
+    w = copy.deepcopy(pkg.synthetic.WORKLOADS[name])
+    w.widths = list(widths)
+    return w
+
+
+@pytest.mark.parametrize("widths,N,K", [([231, 256, 256, 1], 300, 4), ([231, 264, 512, 2], 77, 3),
+                                        ([231, 512, 1], 129, 2)])
+def test_tc_forward_matches_oracle_and_fp32_path(pkg, oracle, widths, N, K):
+    w = wide(pkg, widths)
+    xs, ys = pkg.synthetic.make_data(w, N, K)
+    om = oracle_model(oracle, w.widths, True, 5)
+    rng = np.random.default_rng(9)
+    om.ln_scale = rng.uniform(0.5, 1.5, w.F).astype(np.float32)
+    om.ln_bias = (0.1 * rng.normal(size=w.F)).astype(np.float32)
+    om.b = [(0.1 * rng.normal(size=b.shape)).astype(np.float32) for b in om.b]
+    flat = oracle.flatten_params(om)
+    tgt = "isa" if widths[-1] > 1 else "shiftscale"
+    tc = make_iso(pkg, w, xs, ys, flat, target=tgt, gemm="tc")
+    fp = make_iso(pkg, w, xs, ys, flat, target=tgt, gemm="fp32")
+    xsf, ysf = oracle_features(oracle, w, xs, ys)
+    chi_ref = oracle.forward(om, xsf)
+    chi_tc, chi_fp = records(pkg.chis(tc)), records(pkg.chis(fp))
+    assert np.allclose(chi_fp, chi_ref, rtol=TOL_CHI, atol=1e-5)
+    assert np.allclose(chi_tc, chi_ref, rtol=TOL_CHI, atol=5e-5), np.abs(chi_tc - chi_ref).max()
+    k_ref = oracle.expectation(om, ysf)
+    assert np.allclose(records(pkg.koopman(tc)), k_ref, rtol=TOL_CHI, atol=5e-5)
+
+
+@pytest.mark.parametrize("opt", ["adam", "nesterov"])
+def test_tc_one_iteration_parity(pkg, oracle, opt):
+    r = run_pair(pkg, oracle, "c1", N=512, K=3, minibatch=128, n_iter=1, opt=opt, gemm="tc",
+                 widths=[231, 256, 320, 1])
+    assert np.allclose(r["target_lib"], r["target_ref"], atol=5e-4)
+    assert np.allclose(r["loss_lib"], r["loss_ref"], rtol=2e-3)
+    assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=1e-3, atol=1e-3)
+    scale = np.abs(r["flat_ref"]).max()
+    assert np.abs(r["flat_lib"] - r["flat_ref"]).max() < 2e-3 * scale
+
+
+def test_tc_gradient_first_step(pkg, oracle):
+    # recover the gradient from one Nesterov step (see test_first_step_gradient_through_params)
+    w = wide(pkg, [231, 256, 256, 1])
+    N = 200
+    xs, ys = pkg.synthetic.make_data(w, N, 2)
+    om = oracle_model(oracle, w.widths, True, 5)
+    rng = np.random.default_rng(2)
+    om.ln_scale = rng.uniform(0.5, 1.5, w.F).astype(np.float32)
+    om.ln_bias = (0.1 * rng.normal(size=w.F)).astype(np.float32)
+    flat0 = oracle.flatten_params(om)
+    iso = make_iso(pkg, w, xs, ys, flat0, minibatch=0, gemm="tc")
+    pkg.isotarget(iso)
+    pkg.train_batch_(iso, np.arange(1, N + 1))
+    g_lib = (flat0 - iso.engine.download_params()) / (1.9e-3) - 1e-4 * flat0
+    xsf, ysf = oracle_features(oracle, w, xs, ys)
+    t = oracle.isotarget_shiftscale(om, xsf, ysf)
+    _, g_ref = oracle.batch_loss_and_grad(om, xsf, t, None)
+    err = np.abs(g_lib - g_ref).max() / np.abs(g_ref).max()
+    assert err < 5e-3, err
+
+
+def test_tc_large_batch_split_k(pkg, oracle):
+    r = run_pair(pkg, oracle, "c1", N=8192, K=1, minibatch=0, n_iter=1, opt="adam", gemm="tc",
+                 widths=[231, 256, 256, 1])
+    assert np.allclose(r["loss_lib"], r["loss_ref"], rtol=2e-3)
+    assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=1e-3, atol=1e-3)
+
+
+def test_tc_nd_target_iteration(pkg, oracle):
+    r = run_pair(pkg, oracle, "c4", N=400, K=3, minibatch=100, n_iter=2, opt="adam", target="pinv", gemm="tc",
+                 widths=[231, 256, 256, 3])
+    assert np.allclose(r["loss_lib"], r["loss_ref"], rtol=1e-2)
+    assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=2e-3, atol=2e-3)
+
+
+def test_tc_mode_rejects_narrow_nets(pkg):
+    model = pkg.pairnet(n=231)
+    with pytest.raises(pkg.IsokannError):
+        pkg.Engine(model, pkg.NesterovRegularized(), "allpairs", 22, gemm="tc")
