@@ -145,6 +145,7 @@ struct TcParams {
   int64_t ldo;
   float *out_f32;       // fp32 output (+ split-K slices of M*ldc)
   int64_t ldc;
+  int f32_vec;          // fp32 output is 16-byte aligned with a 16-byte multiple pitch: float4 stores
   const __nv_bfloat16 *z_hi, *z_lo;  // EPI_MULDACT: activation outputs (split), leading dimension ldz
   int64_t ldz;
 };
@@ -275,7 +276,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         if (!row_ok) continue;
         if (p.epi == TC_EPI_F32) {
           float *dst = p.out_f32 + (int64_t)split * p.M * p.ldc + row * p.ldc + col0;
-          if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
+          if (col0 + 32 <= p.N && p.f32_vec) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4 *>(dst + j) =
@@ -400,6 +401,7 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   p.bias = g.bias;
   p.out_hi = g.out_hi; p.out_lo = g.out_lo; p.ldo = g.ldo;
   p.out_f32 = g.out_f32; p.ldc = g.ldc;
+  p.f32_vec = (((uintptr_t)g.out_f32 & 15) == 0 && (g.ldc & 3) == 0 && (((int64_t)g.M * g.ldc) & 3) == 0) ? 1 : 0;
   p.z_hi = g.z_hi; p.z_lo = g.z_lo; p.ldz = g.ldz;
   if (g.epi != TC_EPI_F32)
     IK_REQUIRE(g.ldo % 8 == 0 && g.ldo >= (int64_t)p.n_tiles * 0 + ((g.N + 31) / 32) * 32, ISOKANN_BAD_ARGUMENT,
