@@ -139,12 +139,15 @@ void ensure_folded(Ctx &c) {
 
 // featurize (+ parameter-free LayerNorm) M records and run all Dense layers; results stay in
 // c.act[0..L] (row-major M x width).  `in` holds coordinate records (in_is_coords) or features.
-void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords);
+void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords,
+                     bool keep);
 
-void forward_rows(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords) {
+// keep: the backward pass will need every layer's activations (training step)
+void forward_rows(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords,
+                  bool keep = false) {
   if (M <= 0) return;
   if (c.tc) {
-    forward_rows_tc(c, in, gather, goff, M, in_is_coords);
+    forward_rows_tc(c, in, gather, goff, M, in_is_coords, keep);
     return;
   }
   ensure_act(c, M);
@@ -201,26 +204,40 @@ void ensure_tc_weights(Ctx &c) {
   c.tc_weights_valid = true;
 }
 
-void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords) {
+void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords,
+                     bool keep) {
   TcState &t = *c.tcs;
   tc_ensure_rows(c, M);
   ensure_tc_weights(c);
   const bool pairs = in_is_coords && c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
   launch_featurize_split(c, in, gather, goff, M, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0]);
+  const int last = c.L - 1;
+  const float *seg_last = c.params.p + c.off_w[last];
   for (int l = 0; l + 1 < c.L; ++l) {
     const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
     TcGemm g{};
     g.a_hi = t.act[l].hi.p; g.a_lo = t.act[l].lo.p; g.lda = t.wp[l];
     g.b_hi = t.wF[l].hi.p; g.b_lo = t.wF[l].lo.p; g.ldb = t.wp[l];
     g.M = (int)M; g.N = fout; g.K = fin;
-    g.epi = TC_EPI_BIAS_ACT_SPLIT; g.act = c.cfg.activation;
+    g.act = c.cfg.activation;
     g.bias = layer_segment(c, l) + (int64_t)fin * fout;
-    g.out_hi = t.act[l + 1].hi.p; g.out_lo = t.act[l + 1].lo.p; g.ldo = t.wp[l + 1];
     g.splits = 1;
+    if (l + 2 == c.L && !keep) {
+      // inference: the thin last layer is folded into this GEMM's epilogue, z_{L-1} never hits HBM
+      const int slots = 2 * cdiv(fout, 256);
+      t.dot_partial.ensure((size_t)M * slots * c.d);
+      g.epi = TC_EPI_BIAS_ACT_DOT;
+      g.w_last = seg_last; g.dot_out = t.dot_partial.p; g.d = c.d;
+      launch_tc_gemm(c, g);
+      launch_dot_finish(c, t.dot_partial.p, M, slots, c.d, seg_last + (int64_t)fout * c.d, c.cfg.last_activation,
+                        c.act[c.L].p);
+      return;
+    }
+    g.epi = TC_EPI_BIAS_ACT_SPLIT;
+    g.out_hi = t.act[l + 1].hi.p; g.out_lo = t.act[l + 1].lo.p; g.ldo = t.wp[l + 1];
     launch_tc_gemm(c, g);
   }
-  const int l = c.L - 1;
-  launch_thin_forward(c, t.act[l].hi.p, t.act[l].lo.p, M, c.cfg.widths[l], t.wp[l], c.params.p + c.off_w[l], c.d,
+  launch_thin_forward(c, t.act[last].hi.p, t.act[last].lo.p, M, c.cfg.widths[last], t.wp[last], seg_last, c.d,
                       c.cfg.last_activation, c.act[c.L].p);
 }
 
@@ -628,7 +645,7 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
   if (Bloc == 0) {
     IK_CUDA(cudaMemsetAsync(c.grads.p, 0, (size_t)(c.P + 4) * sizeof(float), c.stream));
   } else {
-    forward_rows(c, c.xs, c.perm_dev.p, s0, Bloc, true);
+    forward_rows(c, c.xs, c.perm_dev.p, s0, Bloc, true, true);
     c.delta_a.ensure((size_t)Bloc * c.maxw);
     c.delta_b.ensure((size_t)Bloc * c.maxw);
     float *cur = c.delta_a.p, *other = c.delta_b.p;
@@ -941,6 +958,7 @@ int32_t isokann_destroy(isokann_ctx *c) {
     c->tcs->deltaT.release();
     c->tcs->delta[0].release();
     c->tcs->delta[1].release();
+    c->tcs->dot_partial.release();
     delete c->tcs;
   }
   c->pairs.release();

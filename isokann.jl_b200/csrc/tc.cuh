@@ -6,7 +6,7 @@
 
 namespace ik {
 
-enum { TC_EPI_BIAS_ACT_SPLIT = 0, TC_EPI_F32 = 1, TC_EPI_MULDACT_SPLIT = 2 };
+enum { TC_EPI_BIAS_ACT_SPLIT = 0, TC_EPI_F32 = 1, TC_EPI_MULDACT_SPLIT = 2, TC_EPI_BIAS_ACT_DOT = 3 };
 
 // D[M x N] = A[M x K] * B[N x K]^T with A, B given as bf16 (hi, lo) pairs, K contiguous
 struct TcGemm {
@@ -23,6 +23,9 @@ struct TcGemm {
   int64_t ldc;
   const __nv_bfloat16 *z_hi, *z_lo;   // TC_EPI_MULDACT_SPLIT
   int64_t ldz;
+  const float *w_last;                // TC_EPI_BIAS_ACT_DOT: fused last (thin) layer, weights [N x d]
+  float *dot_out;                     // partial chi [M x 2*ceil(N/256) x d]
+  int d;
   int splits;
 };
 
@@ -52,6 +55,7 @@ struct TcState {
   std::vector<SplitBuf> wD;    // dgrad operand of layer l   (l = 1..L-2): [w_l x wp_{l+1}]
   SplitBuf actT, deltaT;       // transposed activation (+ ones row) / delta of the current layer
   SplitBuf delta[2];           // row-major delta ping-pong
+  DevBuf<float> dot_partial;   // fused last layer: partial chi per 128-column slot
   std::vector<int> wp;         // padded widths
   int64_t rows = 0, train_rows = 0;
 };
@@ -74,6 +78,9 @@ void launch_thin_forward(Ctx &c, const __nv_bfloat16 *z_hi, const __nv_bfloat16 
 void launch_thin_dgrad(Ctx &c, const float *delta, int64_t M, int d, const float *seg, int fin,
                        const __nv_bfloat16 *z_hi, const __nv_bfloat16 *z_lo, int64_t ldz, int act,
                        __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ldo);
+// chi[m, a] = act(sum_s partial[m, s, a] + b[a]) -- finishes the fused last layer
+void launch_dot_finish(Ctx &c, const float *partial, int64_t M, int slots, int d, const float *bias, int act,
+                       float *chi);
 // grad[(fin+1) x d] = [z, 1]^T * delta from the transposed split activation zT[(fin+1) x ldt]
 void launch_thin_wgrad(Ctx &c, const __nv_bfloat16 *zt_hi, const __nv_bfloat16 *zt_lo, int64_t ldt, int fin, int64_t M,
                        const float *delta, int d, float *grad);

@@ -15,7 +15,7 @@ __device__ __forceinline__ float bflo(uint32_t w) { return __uint_as_float(w << 
 __device__ __forceinline__ float bfhi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 __device__ __forceinline__ float act_f(float a, int kind) {
   switch (kind) {
-    case ISOKANN_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-a));
+    case ISOKANN_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-a));
     case ISOKANN_ACT_TANH: return tanhf(a);
     case ISOKANN_ACT_RELU: return fmaxf(a, 0.f);
     default: return a;
@@ -233,7 +233,30 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const __nv_bfloat16 *__
   }
 }
 
+__global__ void dot_finish_kernel(const float *__restrict__ partial, int64_t M, int slots, int d,
+                                  const float *__restrict__ bias, int act, float *__restrict__ chi) {
+  const int64_t total = M * d;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / d;
+    const int a = (int)(t - m * d);
+    float s = 0.f;
+    for (int k = 0; k < slots; ++k) s += partial[(m * slots + k) * d + a];
+    chi[t] = act_f(s + __ldg(bias + a), act);
+  }
+}
+
 }  // namespace
+
+void launch_dot_finish(Ctx &c, const float *partial, int64_t M, int slots, int d, const float *bias, int act,
+                       float *chi) {
+  if (M <= 0) return;
+  int grid = (int)std::min<int64_t>((M * d + 255) / 256, (int64_t)c.num_sms * 8);
+  c.timer.begin(KC_REDUCE, c.stream);
+  dot_finish_kernel<<<grid, 256, 0, c.stream>>>(partial, M, slots, d, bias, act, chi);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_REDUCE);
+}
 
 void launch_transpose_split(Ctx &c, const __nv_bfloat16 *in_hi, const __nv_bfloat16 *in_lo, int64_t rows, int cols,
                             int64_t ld_in, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld_out,

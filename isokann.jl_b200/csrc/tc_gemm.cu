@@ -33,7 +33,8 @@ constexpr int A_TILE = BM * BK * 2;  // bytes of one bf16 A tile
 constexpr int B_TILE = BN * BK * 2;
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // 96 KiB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int NTHREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NTHREADS = 64 + 32 * EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
 constexpr uint32_t TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -50,7 +51,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // bounded spin: a protocol bug must surface as a trap, never as a hung GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -60,7 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (++spins > 200000000u) __trap();  // try_wait suspends in hardware between probes
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
@@ -111,7 +112,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 __device__ __forceinline__ float act_fwd(float a, int kind) {
   switch (kind) {
-    case ISOKANN_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-a));
+    case ISOKANN_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-a));
     case ISOKANN_ACT_TANH: return tanhf(a);
     case ISOKANN_ACT_RELU: return fmaxf(a, 0.f);
     default: return a;
@@ -127,11 +128,12 @@ __device__ __forceinline__ float dact_o(float z, int kind) {
 }
 
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-  const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-  const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-  hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);  // .x (low half) = x0
+  hi = *reinterpret_cast<const uint32_t *>(&h2);
+  const float r0 = x0 - __uint_as_float(hi << 16);
+  const float r1 = x1 - __uint_as_float(hi & 0xFFFF0000u);
+  const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+  lo = *reinterpret_cast<const uint32_t *>(&l2);
 }
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
@@ -145,11 +147,15 @@ struct TcParams {
   int64_t ldo;
   float *out_f32;       // fp32 output (+ split-K slices of M*ldc)
   int64_t ldc;
+  const float *w_last;  // TC_EPI_BIAS_ACT_DOT: last-layer weights [N x d] row-major
+  float *dot_out;       // partial chi [M x dot_slots x d]
+  int d, dot_slots;
   int f32_vec;          // fp32 output is 16-byte aligned with a 16-byte multiple pitch: float4 stores
   const __nv_bfloat16 *z_hi, *z_lo;  // EPI_MULDACT: activation outputs (split), leading dimension ldz
   int64_t ldz;
 };
 
+template <int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, TcParams p) {
@@ -173,7 +179,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);
+      mbar_init(bar_tempty + 8 * a, EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -253,8 +259,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // a warp may only touch TMEM lanes [32*(warp%4), +32): two warps share each lane quarter and
+    // take one 128-column half of the accumulator each
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int split = t / (p.m_tiles * p.n_tiles);
@@ -267,67 +276,122 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       const int64_t row = (int64_t)mb * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      float dot[kMaxD];
+#pragma unroll
+      for (int a = 0; a < kMaxD; ++a) dot[a] = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
         const int col0 = nb * BN + c;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr0 + c, r);
         if (!row_ok) continue;
-        if (p.epi == TC_EPI_F32) {
+        const bool full = col0 + 32 <= p.N;
+        if (EPI == TC_EPI_F32) {
           float *dst = p.out_f32 + (int64_t)split * p.M * p.ldc + row * p.ldc + col0;
-          if (col0 + 32 <= p.N && p.f32_vec) {
+          if (full && p.f32_vec) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4 *>(dst + j) =
                   make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                               __uint_as_float(r[j + 3]));
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]);
           }
-        } else {
-          float v[32];
+          continue;
+        }
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.epi == TC_EPI_BIAS_ACT_SPLIT) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (EPI == TC_EPI_MULDACT_SPLIT) {
+          const uint4 *zh = reinterpret_cast<const uint4 *>(p.z_hi + row * p.ldz + col0);
+          const uint4 *zl = reinterpret_cast<const uint4 *>(p.z_lo + row * p.ldz + col0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 h = __ldg(zh + q), l = __ldg(zl + q);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float z0 = bf16lo(hw[e]) + bf16lo(lw[e]);
+              const float z1 = bf16hi(hw[e]) + bf16hi(lw[e]);
+              v[q * 8 + 2 * e] *= dact_o(z0, p.act);
+              v[q * 8 + 2 * e + 1] *= dact_o(z1, p.act);
+            }
+          }
+        } else {  // bias + activation
+          if (p.bias) {
+            if (full) {
+              const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0);
+              if ((reinterpret_cast<uintptr_t>(b4) & 15) == 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 b = __ldg(b4 + q);
+                  v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + col0 + j);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+            }
+          }
+          if (p.act == ISOKANN_ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
+          } else if (p.act != ISOKANN_ACT_IDENTITY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act);
+          }
+        }
+        if (EPI == TC_EPI_BIAS_ACT_DOT) {
+          // chi partial: sum over this warp's columns of z[col] * W_last[col, a]
+          if (p.d == 1 && full && ((reinterpret_cast<uintptr_t>(p.w_last + col0) & 15) == 0)) {
+            const float4 *w4 = reinterpret_cast<const float4 *>(p.w_last + col0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 w = __ldg(w4 + q);
+              dot[0] = fmaf(v[4 * q], w.x, dot[0]);
+              dot[0] = fmaf(v[4 * q + 1], w.y, dot[0]);
+              dot[0] = fmaf(v[4 * q + 2], w.z, dot[0]);
+              dot[0] = fmaf(v[4 * q + 3], w.w, dot[0]);
+            }
+          } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float b = (p.bias && col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
-              v[j] = act_fwd(v[j] + b, p.act);
-            }
-          } else {  // TC_EPI_MULDACT_SPLIT
-            const uint4 *zh = reinterpret_cast<const uint4 *>(p.z_hi + row * p.ldz + col0);
-            const uint4 *zl = reinterpret_cast<const uint4 *>(p.z_lo + row * p.ldz + col0);
+              if (col0 + j < p.N) {
+                const float *wl = p.w_last + (int64_t)(col0 + j) * p.d;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 h = __ldg(zh + q), l = __ldg(zl + q);
-              const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float z0 = bf16lo(hw[e]) + bf16lo(lw[e]);
-                const float z1 = bf16hi(hw[e]) + bf16hi(lw[e]);
-                v[q * 8 + 2 * e] *= dact_o(z0, p.act);
-                v[q * 8 + 2 * e + 1] *= dact_o(z1, p.act);
+                for (int a = 0; a < kMaxD; ++a)
+                  if (a < p.d) dot[a] = fmaf(v[j], __ldg(wl + a), dot[a]);
               }
             }
           }
-          // columns >= N inside the padded leading dimension are written as zeros
-          uint32_t ph[16], pl[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float x0 = (col0 + 2 * j < p.N) ? v[2 * j] : 0.f;
-            const float x1 = (col0 + 2 * j + 1 < p.N) ? v[2 * j + 1] : 0.f;
-            split_pair(x0, x1, ph[j], pl[j]);
-          }
-          uint4 *dh = reinterpret_cast<uint4 *>(p.out_hi + row * p.ldo + col0);
-          uint4 *dl = reinterpret_cast<uint4 *>(p.out_lo + row * p.ldo + col0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            dh[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-            dl[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
-          }
+          continue;
         }
+        if (!full) {  // columns >= N inside the padded leading dimension are written as zeros
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j >= p.N) v[j] = 0.f;
+        }
+        uint32_t ph[16], pl[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+        uint4 *dh = reinterpret_cast<uint4 *>(p.out_hi + row * p.ldo + col0);
+        uint4 *dl = reinterpret_cast<uint4 *>(p.out_lo + row * p.ldo + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          dh[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+          dl[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+        }
+      }
+      if (EPI == TC_EPI_BIAS_ACT_DOT && row_ok) {
+        float *dst = p.dot_out + (row * p.dot_slots + (nb * 2 + half)) * p.d;
+        for (int a = 0; a < p.d; ++a) dst[a] = dot[a];
       }
       tc_fence_before();
       __syncwarp();
@@ -379,7 +443,10 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
   static bool attr = false;
   if (!attr) {
-    IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_BIAS_ACT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_MULDACT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_BIAS_ACT_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }
   alignas(64) CUtensorMap mah, mal, mbh, mbl;
@@ -403,7 +470,8 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   p.out_f32 = g.out_f32; p.ldc = g.ldc;
   p.f32_vec = (((uintptr_t)g.out_f32 & 15) == 0 && (g.ldc & 3) == 0 && (((int64_t)g.M * g.ldc) & 3) == 0) ? 1 : 0;
   p.z_hi = g.z_hi; p.z_lo = g.z_lo; p.ldz = g.ldz;
-  if (g.epi != TC_EPI_F32)
+  p.w_last = g.w_last; p.dot_out = g.dot_out; p.d = g.d; p.dot_slots = 2 * p.n_tiles;
+  if (g.epi == TC_EPI_BIAS_ACT_SPLIT || g.epi == TC_EPI_MULDACT_SPLIT)
     IK_REQUIRE(g.ldo % 8 == 0 && g.ldo >= (int64_t)p.n_tiles * 0 + ((g.N + 31) / 32) * 32, ISOKANN_BAD_ARGUMENT,
                "split output needs a leading dimension padded to 32 columns");
   if (g.epi == TC_EPI_MULDACT_SPLIT)
@@ -411,7 +479,20 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = std::min(total, c.num_sms);
   c.timer.begin(KC_GEMM, c.stream);
-  tc_gemm_kernel<<<grid, NTHREADS, SMEM_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);
+  switch (g.epi) {
+    case TC_EPI_BIAS_ACT_SPLIT:
+      tc_gemm_kernel<TC_EPI_BIAS_ACT_SPLIT><<<grid, NTHREADS, SMEM_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);
+      break;
+    case TC_EPI_F32:
+      tc_gemm_kernel<TC_EPI_F32><<<grid, NTHREADS, SMEM_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);
+      break;
+    case TC_EPI_MULDACT_SPLIT:
+      tc_gemm_kernel<TC_EPI_MULDACT_SPLIT><<<grid, NTHREADS, SMEM_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);
+      break;
+    default:
+      tc_gemm_kernel<TC_EPI_BIAS_ACT_DOT><<<grid, NTHREADS, SMEM_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);
+      break;
+  }
   c.timer.end(c.stream);
   IK_CUDA(cudaGetLastError());
   c.count_launch(KC_GEMM, 2.0 * (double)g.M * (double)g.N * (double)g.K);
