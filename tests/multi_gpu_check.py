@@ -1,0 +1,75 @@
+"""torchrun worker: N-rank run of the library (start points sharded, NCCL all-gather of K-chi and
+all-reduce of gradients) must reproduce the single-GPU run of the same workload.
+
+    torchrun --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    uid = pkg.parallel.broadcast_unique_id(rank)
+    import copy
+    failures = []
+    for name, widths, target, N, K, B, gemm in [("c1", None, "shiftscale", 1003, 3, 250, "auto"),
+                                                ("c4", [231, 38, 6, 3], "pinv", 777, 2, 128, "auto"),
+                                                ("c4", [231, 38, 6, 2], "isa", 640, 2, 0, "auto"),
+                                                ("c1", [231, 256, 256, 1], "shiftscale", 900, 2, 300, "tc")]:
+        w = copy.deepcopy(pkg.synthetic.WORKLOADS[name])
+        if widths:
+            w.widths = widths
+        xs, ys = pkg.synthetic.make_data(w, N, K)
+        perms = pkg.synthetic.make_perms(w, N, 3)
+        model = pkg.densenet(w.widths, layernorm=True, rng=np.random.default_rng(7))
+        flat0 = model.flat()
+        tobj = {"shiftscale": pkg.TransformShiftscale, "isa": pkg.TransformISA, "pinv": pkg.TransformPseudoInv}[target]()
+
+        def make(comm):
+            m = pkg.Chain(list(w.widths), True).load_flat(flat0)
+            data = pkg.SimulationData(xs, ys, featurizer=pkg.FeaturesAll())
+            return pkg.Iso(data, opt=pkg.AdamRegularized(), model=m, target=tobj, minibatch=B, device=local, gemm=gemm,
+                           comm=comm)
+        multi = make((world, rank, uid))
+        pkg.run_(multi, 3, perms=perms)
+        chi_m = pkg.chis(multi)
+        flat_m = multi.engine.download_params()
+        single = make(None)
+        pkg.run_(single, 3, perms=perms)
+        chi_s = pkg.chis(single)
+        flat_s = single.engine.download_params()
+        tol = 2e-3 if gemm == "tc" or target != "shiftscale" else 2e-4
+        ok = (np.allclose(multi.losses, single.losses, rtol=tol) and np.allclose(chi_m, chi_s, rtol=tol, atol=tol)
+              and np.abs(flat_m - flat_s).max() < tol * np.abs(flat_s).max())
+        st = multi.engine.stats()
+        if not ok or st["nccl_calls"] == 0:
+            failures.append((name, target, multi.losses, single.losses, float(np.abs(chi_m - chi_s).max())))
+        # every rank must hold identical parameters
+        t = torch.from_numpy(flat_m.copy()).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        if not torch.equal(t, ref):
+            failures.append((name, "replicas diverged"))
+    flag = torch.tensor([len(failures)], device="cuda")
+    dist.all_reduce(flag)
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "OK" if flag.item() == 0 else f"FAILED {failures}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
