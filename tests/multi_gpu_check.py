@@ -21,7 +21,6 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    uid = pkg.parallel.broadcast_unique_id(rank)
     import copy
     failures = []
     for name, widths, target, N, K, B, gemm in [("c1", None, "shiftscale", 1003, 3, 250, "auto"),
@@ -42,6 +41,7 @@ def main():
             data = pkg.SimulationData(xs, ys, featurizer=pkg.FeaturesAll())
             return pkg.Iso(data, opt=pkg.AdamRegularized(), model=m, target=tobj, minibatch=B, device=local, gemm=gemm,
                            comm=comm)
+        uid = pkg.parallel.broadcast_unique_id(rank)      # a communicator needs its own fresh id
         multi = make((world, rank, uid))
         pkg.run_(multi, 3, perms=perms)
         chi_m = pkg.chis(multi)
