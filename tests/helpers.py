@@ -20,19 +20,20 @@ def oracle_features(oracle, w, xs, ys):
     return oracle.flatpairdists(records(xs)), oracle.flatpairdists(records(ys))
 
 
-def make_iso(pkg, w, xs, ys, flat, opt="nesterov", target=None, minibatch=None, **kw):
+def make_iso(pkg, w, xs, ys, flat, opt="nesterov", target=None, minibatch=None, target_opts=None, **kw):
     feat = pkg.FeaturesAll() if w.featurizer == "allpairs" else pkg.FeaturesCoords()
     data = pkg.SimulationData(xs, ys, featurizer=feat)
     model = pkg.Chain(list(w.widths), w.layernorm).load_flat(flat)
     rule = pkg.AdamRegularized() if opt == "adam" else pkg.NesterovRegularized()
     tk = target or w.target
-    tobj = {"shiftscale": pkg.TransformShiftscale, "isa": pkg.TransformISA, "pinv": pkg.TransformPseudoInv}[tk]()
+    tobj = {"shiftscale": pkg.TransformShiftscale, "isa": pkg.TransformISA,
+            "pinv": pkg.TransformPseudoInv}[tk](**(target_opts or {}))
     return pkg.Iso(data, opt=rule, model=model, target=tobj, minibatch=w.minibatch if minibatch is None else minibatch,
                    **kw)
 
 
 def run_pair(pkg, oracle, name, N, K, minibatch, n_iter, opt="nesterov", target=None, epochs=1, gemm="auto",
-             widths=None):
+             widths=None, target_opts=None):
     """one workload through both implementations; returns losses, final chi, first target, stats"""
     import copy
     w = copy.deepcopy(pkg.synthetic.WORKLOADS[name])
@@ -44,7 +45,8 @@ def run_pair(pkg, oracle, name, N, K, minibatch, n_iter, opt="nesterov", target=
     om = oracle_model(oracle, w.widths, w.layernorm, w.seed + 1)
     flat0 = oracle.flatten_params(om)
 
-    iso = make_iso(pkg, w, xs, ys, flat0, opt, tk, minibatch, gemm=gemm)
+    topts = dict(target_opts or {})
+    iso = make_iso(pkg, w, xs, ys, flat0, opt, tk, minibatch, target_opts=topts, gemm=gemm)
     t_lib = pkg.isotarget(iso)                       # target of the first iteration (before any training)
     chi0_lib = pkg.chis(iso)
     iso.engine.reset_stats()
@@ -56,9 +58,9 @@ def run_pair(pkg, oracle, name, N, K, minibatch, n_iter, opt="nesterov", target=
     xsf, ysf = oracle_features(oracle, w, xs, ys)
     cfg = oracle.OptConfig(kind=opt)
     st = oracle.opt_init(cfg, flat0.size)
-    t_ref = oracle.isotarget(tk, om, xsf, ysf)
+    t_ref = oracle.isotarget(tk, om, xsf, ysf, **topts)
     chi0_ref = oracle.forward(om, xsf)
-    losses_ref = oracle.run(om, xsf, ysf, cfg, st, n_iter, minibatch, list(perms), tk, epochs)
+    losses_ref = oracle.run(om, xsf, ysf, cfg, st, n_iter, minibatch, list(perms), tk, epochs, **topts)
     chi_ref = oracle.forward(om, xsf)
     return {
         "loss_lib": np.array(iso.losses), "loss_ref": np.array(losses_ref),
