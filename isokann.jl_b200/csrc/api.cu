@@ -141,6 +141,7 @@ void ensure_folded(Ctx &c) {
 // c.act[0..L] (row-major M x width).  `in` holds coordinate records (in_is_coords) or features.
 void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords,
                      bool keep);
+void forward_rows_tcn(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords);
 
 // keep: the backward pass will need every layer's activations (training step)
 void forward_rows(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords,
@@ -148,6 +149,10 @@ void forward_rows(Ctx &c, const float *in, const int64_t *gather, int64_t goff, 
   if (M <= 0) return;
   if (c.tc) {
     forward_rows_tc(c, in, gather, goff, M, in_is_coords, keep);
+    return;
+  }
+  if (c.tcn && !keep) {
+    forward_rows_tcn(c, in, gather, goff, M, in_is_coords);
     return;
   }
   ensure_act(c, M);
@@ -181,10 +186,19 @@ bool tc_eligible(const isokann_config &g) {
   return true;
 }
 
+// narrow nets (default pairnets): first layer on tensor cores, the rest (widths <= 16) in its epilogue
+bool tcn_eligible(const isokann_config &g) {
+  if (g.n_layers < 2 || g.n_layers > 4) return false;
+  if (g.widths[0] < 64 || g.widths[1] > 128 || g.widths[1] < 1) return false;
+  for (int l = 2; l <= g.n_layers; ++l)
+    if (g.widths[l] > 16) return false;
+  return g.widths[g.n_layers] <= kMaxD;
+}
+
 void tc_ensure_rows(Ctx &c, int64_t rows) {
   TcState &t = *c.tcs;
   if (rows > t.rows) {
-    for (int l = 0; l < c.L; ++l) t.act[l].ensure(rows, t.wp[l]);
+    for (int l = 0; l < (c.tcn ? 1 : c.L); ++l) t.act[l].ensure(rows, t.wp[l]);
     c.act[c.L].ensure((size_t)rows * c.d);
     t.rows = rows;
   }
@@ -194,7 +208,7 @@ void ensure_tc_weights(Ctx &c) {
   if (c.tc_weights_valid) return;
   ensure_folded(c);
   TcState &t = *c.tcs;
-  for (int l = 0; l + 1 < c.L; ++l) {
+  for (int l = 0; l + 1 < (c.tcn ? 2 : c.L); ++l) {
     const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
     t.wF[l].ensure(fout, t.wp[l]);
     if (l > 0) t.wD[l].ensure(fin, t.wp[l + 1]);
@@ -239,6 +253,30 @@ void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t gof
   }
   launch_thin_forward(c, t.act[last].hi.p, t.act[last].lo.p, M, c.cfg.widths[last], t.wp[last], seg_last, c.d,
                       c.cfg.last_activation, c.act[c.L].p);
+}
+
+void forward_rows_tcn(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords) {
+  TcState &t = *c.tcs;
+  tc_ensure_rows(c, M);
+  ensure_tc_weights(c);
+  const bool pairs = in_is_coords && c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
+  launch_featurize_split(c, in, gather, goff, M, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0]);
+  const int fin = c.cfg.widths[0], fout = c.cfg.widths[1];
+  TcGemm g{};
+  g.a_hi = t.act[0].hi.p; g.a_lo = t.act[0].lo.p; g.lda = t.wp[0];
+  g.b_hi = t.wF[0].hi.p; g.b_lo = t.wF[0].lo.p; g.ldb = t.wp[0];
+  g.M = (int)M; g.N = fout; g.K = fin;
+  g.act = c.cfg.activation;
+  g.bias = layer_segment(c, 0) + (int64_t)fin * fout;
+  g.epi = TC_EPI_TAIL;
+  g.tail.nl = c.L - 1;
+  g.tail.act = c.cfg.activation;
+  g.tail.last_act = c.cfg.last_activation;
+  for (int l = 1; l <= c.L; ++l) g.tail.w[l - 1] = c.cfg.widths[l];
+  for (int l = 1; l < c.L; ++l) g.tail.seg[l - 1] = c.params.p + c.off_w[l];
+  g.chi_out = c.act[c.L].p;
+  g.splits = 1;
+  launch_tc_gemm(c, g);
 }
 
 // backward + gradient assembly of one minibatch slice on the tensor-core path; forward_rows_tc and
@@ -907,7 +945,8 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
       IK_REQUIRE(tc_eligible(*cfg), ISOKANN_BAD_ARGUMENT,
                  "ISOKANN_GEMM_TC needs >= 2 layers, hidden widths >= 256, input width >= 64, output <= 8");
     c->tc = cfg->gemm_mode != ISOKANN_GEMM_FP32 && tc_eligible(*cfg);
-    if (c->tc) {
+    c->tcn = !c->tc && cfg->gemm_mode == ISOKANN_GEMM_AUTO && tcn_eligible(*cfg);
+    if (c->tc || c->tcn) {
       c->tcs = new TcState;
       c->tcs->act.resize(c->L);
       c->tcs->wF.resize(c->L);

@@ -173,6 +173,7 @@ struct Ctx {
   float beta_t[2] = {0.f, 0.f};
   bool folded_valid = false;  // folded1 matches the current parameters
   bool tc = false;            // wide Dense layers run on tcgen05 (3xBF16 split)
+  bool tcn = false;           // narrow net: inference forward = one tcgen05 GEMM with the MLP tail in its epilogue
   bool tc_weights_valid = false;
   TcState *tcs = nullptr;
   DevBuf<int2> pairs;  // coordinate offsets (3a, 3b) per feature

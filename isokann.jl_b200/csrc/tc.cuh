@@ -6,7 +6,16 @@
 
 namespace ik {
 
-enum { TC_EPI_BIAS_ACT_SPLIT = 0, TC_EPI_F32 = 1, TC_EPI_MULDACT_SPLIT = 2, TC_EPI_BIAS_ACT_DOT = 3 };
+enum { TC_EPI_BIAS_ACT_SPLIT = 0, TC_EPI_F32 = 1, TC_EPI_MULDACT_SPLIT = 2, TC_EPI_BIAS_ACT_DOT = 3, TC_EPI_TAIL = 4 };
+
+// the Dense layers after the tensor-core layer of a narrow net (e.g. 71 -> 8 -> 1), evaluated per row in
+// the GEMM epilogue: w[0] = GEMM N (<= 128), w[1..nl] <= 16; seg[i] = row-major (w[i]+1) x w[i+1] [W; b]
+struct TcTail {
+  int nl;
+  int w[4];
+  const float *seg[3];
+  int act, last_act;
+};
 
 // D[M x N] = A[M x K] * B[N x K]^T with A, B given as bf16 (hi, lo) pairs, K contiguous
 struct TcGemm {
@@ -26,6 +35,8 @@ struct TcGemm {
   const float *w_last;                // TC_EPI_BIAS_ACT_DOT: fused last (thin) layer, weights [N x d]
   float *dot_out;                     // partial chi [M x 2*ceil(N/256) x d]
   int d;
+  TcTail tail;                        // TC_EPI_TAIL
+  float *chi_out;                     // TC_EPI_TAIL: [M x tail.w[tail.nl]]
   int splits;
 };
 

@@ -32,7 +32,8 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 2;
 constexpr int A_TILE = BM * BK * 2;  // bytes of one bf16 A tile
 constexpr int B_TILE = BN * BK * 2;
 constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // 96 KiB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TAIL_FLOATS = 3072;   // staged tail weights: (128+1)*16 + 17*16 + 17*16 floats at most
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TAIL_FLOATS * 4;
 constexpr int EPI_WARPS = 8;
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
 constexpr uint32_t TMEM_COLS = 512;
@@ -147,6 +148,8 @@ struct TcParams {
   int64_t ldo;
   float *out_f32;       // fp32 output (+ split-K slices of M*ldc)
   int64_t ldc;
+  TcTail tail;          // TC_EPI_TAIL
+  float *chi_out;
   const float *w_last;  // TC_EPI_BIAS_ACT_DOT: last-layer weights [N x d] row-major
   float *dot_out;       // partial chi [M x dot_slots x d]
   int d, dot_slots;
@@ -193,6 +196,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // TC_EPI_TAIL: stage the tail layers' [W; b] in shared memory, rows padded to a multiple of 4 floats
+  float *tailw = reinterpret_cast<float *>(base_ptr + STAGES * STAGE_BYTES + 256);
+  if (EPI == TC_EPI_TAIL) {
+    int off = 0;
+    for (int i = 0; i < p.tail.nl; ++i) {
+      const int rows = p.tail.w[i] + 1, cols = p.tail.w[i + 1], cp = (cols + 3) & ~3;
+      for (int e = threadIdx.x; e < rows * cp; e += blockDim.x) {
+        const int r = e / cp, cc = e - r * cp;
+        tailw[off + e] = cc < cols ? __ldg(p.tail.seg[i] + (int64_t)r * cols + cc) : 0.f;
+      }
+      off += rows * cp;
+    }
+    __syncthreads();
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -279,6 +296,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       float dot[kMaxD];
 #pragma unroll
       for (int a = 0; a < kMaxD; ++a) dot[a] = 0.f;
+      float tl[16];  // TC_EPI_TAIL: pre-activations of the first tail layer
+#pragma unroll
+      for (int a = 0; a < 16; ++a) tl[a] = 0.f;
 #pragma unroll 1
       for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
         const int col0 = nb * BN + c;
@@ -348,6 +368,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
             for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act);
           }
         }
+        if (EPI == TC_EPI_TAIL) {
+          // first tail layer: a[k] += z[col] * W[col, k] with W rows broadcast from shared memory
+          const int cp = (p.tail.w[1] + 3) & ~3;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < p.N) {
+              const float4 *wr = reinterpret_cast<const float4 *>(tailw + (col0 + j) * cp);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (4 * q < cp) {
+                  const float4 w4 = wr[q];
+                  tl[4 * q] = fmaf(v[j], w4.x, tl[4 * q]);
+                  tl[4 * q + 1] = fmaf(v[j], w4.y, tl[4 * q + 1]);
+                  tl[4 * q + 2] = fmaf(v[j], w4.z, tl[4 * q + 2]);
+                  tl[4 * q + 3] = fmaf(v[j], w4.w, tl[4 * q + 3]);
+                }
+              }
+            }
+          }
+          continue;
+        }
         if (EPI == TC_EPI_BIAS_ACT_DOT) {
           // chi partial: sum over this warp's columns of z[col] * W_last[col, a]
           if (p.d == 1 && full && ((reinterpret_cast<uintptr_t>(p.w_last + col0) & 15) == 0)) {
@@ -388,6 +429,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
           dh[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
           dl[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
         }
+      }
+      if (EPI == TC_EPI_TAIL && row_ok && half == 0) {
+        // finish the tail: bias + activation of its first layer, then the remaining (tiny) layers
+        int off = 0;
+        float h[16];
+        {
+          const int cols = p.tail.w[1], cp = (cols + 3) & ~3;
+          const float *brow = tailw + p.tail.w[0] * cp;
+          const int kind = p.tail.nl == 1 ? p.tail.last_act : p.tail.act;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) h[k] = k < cols ? act_fwd(tl[k] + brow[k], kind) : 0.f;
+          off += (p.tail.w[0] + 1) * cp;
+        }
+        for (int i = 1; i < p.tail.nl; ++i) {
+          const int rows = p.tail.w[i], cols = p.tail.w[i + 1], cp = (cols + 3) & ~3;
+          float a2[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) a2[k] = k < cols ? tailw[off + rows * cp + k] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j < rows) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k)
+                if (k < cp) a2[k] = fmaf(h[j], tailw[off + j * cp + k], a2[k]);
+            }
+          }
+          const int kind = i == p.tail.nl - 1 ? p.tail.last_act : p.tail.act;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) h[k] = k < cols ? act_fwd(a2[k], kind) : 0.f;
+          off += (rows + 1) * cp;
+        }
+        const int dd = p.tail.w[p.tail.nl];
+#pragma unroll
+        for (int k = 0; k < kMaxD; ++k)
+          if (k < dd) p.chi_out[row * dd + k] = h[k];
       }
       if (EPI == TC_EPI_BIAS_ACT_DOT && row_ok) {
         float *dst = p.dot_out + (row * p.dot_slots + (nb * 2 + half)) * p.d;
@@ -447,6 +523,7 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
     IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_MULDACT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_BIAS_ACT_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }
   alignas(64) CUtensorMap mah, mal, mbh, mbl;
@@ -470,12 +547,23 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   p.out_f32 = g.out_f32; p.ldc = g.ldc;
   p.f32_vec = (((uintptr_t)g.out_f32 & 15) == 0 && (g.ldc & 3) == 0 && (((int64_t)g.M * g.ldc) & 3) == 0) ? 1 : 0;
   p.z_hi = g.z_hi; p.z_lo = g.z_lo; p.ldz = g.ldz;
+  p.tail = g.tail; p.chi_out = g.chi_out;
   p.w_last = g.w_last; p.dot_out = g.dot_out; p.d = g.d; p.dot_slots = 2 * p.n_tiles;
   if (g.epi == TC_EPI_BIAS_ACT_SPLIT || g.epi == TC_EPI_MULDACT_SPLIT)
     IK_REQUIRE(g.ldo % 8 == 0 && g.ldo >= (int64_t)p.n_tiles * 0 + ((g.N + 31) / 32) * 32, ISOKANN_BAD_ARGUMENT,
                "split output needs a leading dimension padded to 32 columns");
   if (g.epi == TC_EPI_MULDACT_SPLIT)
     IK_REQUIRE(g.ldz % 8 == 0 && g.ldz >= ((g.N + 31) / 32) * 32, ISOKANN_BAD_ARGUMENT, "z leading dimension");
+  if (g.epi == TC_EPI_TAIL) {
+    IK_REQUIRE(g.N <= 128 && g.tail.nl >= 1 && g.tail.nl <= 3 && g.tail.w[0] == g.N, ISOKANN_BAD_ARGUMENT,
+               "tail epilogue needs N <= 128 and 1..3 tail layers");
+    int fl = 0;
+    for (int i = 0; i < g.tail.nl; ++i) {
+      IK_REQUIRE(g.tail.w[i + 1] >= 1 && g.tail.w[i + 1] <= 16, ISOKANN_BAD_ARGUMENT, "tail widths must be <= 16");
+      fl += (g.tail.w[i] + 1) * ((g.tail.w[i + 1] + 3) & ~3);
+    }
+    IK_REQUIRE(fl <= TAIL_FLOATS && g.tail.w[g.tail.nl] <= kMaxD, ISOKANN_BAD_ARGUMENT, "tail too large");
+  }
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = std::min(total, c.num_sms);
   c.timer.begin(KC_GEMM, c.stream);
@@ -488,6 +576,9 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
       break;
     case TC_EPI_MULDACT_SPLIT:
       tc_gemm_kernel<TC_EPI_MULDACT_SPLIT><<<grid, NTHREADS, SMEM_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);
+      break;
+    case TC_EPI_TAIL:
+      tc_gemm_kernel<TC_EPI_TAIL><<<grid, NTHREADS, SMEM_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);
       break;
     default:
       tc_gemm_kernel<TC_EPI_BIAS_ACT_DOT><<<grid, NTHREADS, SMEM_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);

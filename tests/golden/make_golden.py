@@ -22,7 +22,8 @@ import oracle  # noqa: E402
 OUT = Path(__file__).resolve().parent
 
 
-def case(pkg, name, widths, N, K, B, n_iter, opt, target, seed_model):
+def case(pkg, name, widths, N, K, B, n_iter, opt, target, seed_model, topts=None):
+    topts = dict(topts or {})
     import copy
     w = copy.deepcopy(pkg.synthetic.WORKLOADS[name])
     w.widths = list(widths)
@@ -37,14 +38,14 @@ def case(pkg, name, widths, N, K, B, n_iter, opt, target, seed_model):
     perms = pkg.synthetic.make_perms(w, N, n_iter)
     chi0 = oracle.forward(m, xsf)
     kchi0 = oracle.expectation(m, ysf)
-    target0 = oracle.isotarget(target, m, xsf, ysf)
+    target0 = oracle.isotarget(target, m, xsf, ysf, **topts)
     cfg = oracle.OptConfig(kind=opt)
     st = oracle.opt_init(cfg, flat0.size)
-    losses = oracle.run(m, xsf, ysf, cfg, st, n_iter, B, list(perms), target)
+    losses = oracle.run(m, xsf, ysf, cfg, st, n_iter, B, list(perms), target, **topts)
     return dict(xs=np.asarray(xs), ys=np.asarray(ys), features_x=xsf[:8], flat0=flat0, perms=perms, chi0=chi0,
                 kchi0=kchi0, target0=target0, losses=np.array(losses), flat_final=oracle.flatten_params(m),
                 chi_final=oracle.forward(m, xsf), widths=np.array(w.widths), meta=np.array([N, K, B, n_iter]),
-                name=name, opt=opt, target=target)
+                name=name, opt=opt, target=target, topts=np.array(sorted(k for k, v in topts.items() if v is False)))
 
 
 def main():
@@ -54,8 +55,10 @@ def main():
         "adp_shiftscale_adam": ("c1", [231, 38, 6, 1], 48, 3, 16, 3, "adam", "shiftscale", 11),
         "triplewell_smallnet": ("c2", [2, 8, 8, 8, 1], 64, 4, 32, 3, "nesterov", "shiftscale", 12),
         "villin_shiftscale": ("c3", [595, 71, 8, 1], 40, 2, 20, 2, "nesterov", "shiftscale", 13),
-        "adp_pinv_3d": ("c4", [231, 38, 6, 3], 60, 3, 20, 2, "adam", "pinv", 14),
-        "adp_isa_2d": ("c4", [231, 38, 6, 2], 60, 3, 20, 2, "adam", "isa", 15),
+        # N-D targets without the rounding-sensitive choices (Schur vector signs, fixperm ties at random init);
+        # those are covered by tests/test_gpu_parity.py::test_nd_targets on seeds with a clear margin
+        "adp_pinv_3d": ("c4", [231, 38, 6, 3], 60, 3, 20, 2, "adam", "pinv", 14, {"eigenvecs": False, "permute": False}),
+        "adp_isa_2d": ("c4", [231, 38, 6, 2], 60, 3, 20, 2, "adam", "isa", 15, {"permute": False}),
     }
     for key, args in cases.items():
         np.savez_compressed(OUT / f"{key}.npz", **case(pkg, *args))

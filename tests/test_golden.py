@@ -32,9 +32,10 @@ def test_oracle_matches_golden(oracle, pkg, case):
     assert np.allclose(oracle.forward(m, xsf), z["chi0"], rtol=1e-5, atol=1e-6)
     assert np.allclose(oracle.expectation(m, ysf), z["kchi0"], rtol=1e-5, atol=1e-6)
     tk = str(z["target"])
-    assert np.allclose(oracle.isotarget(tk, m, xsf, ysf), z["target0"], rtol=1e-4, atol=1e-4)
+    topts = {str(k): False for k in z["topts"]}
+    assert np.allclose(oracle.isotarget(tk, m, xsf, ysf, **topts), z["target0"], rtol=1e-4, atol=1e-4)
     cfg = oracle.OptConfig(kind=str(z["opt"]))
     st = oracle.opt_init(cfg, z["flat0"].size)
-    losses = oracle.run(m, xsf, ysf, cfg, st, n_iter, B, list(z["perms"]), tk)
+    losses = oracle.run(m, xsf, ysf, cfg, st, n_iter, B, list(z["perms"]), tk, **topts)
     assert np.allclose(losses, z["losses"], rtol=1e-4)
     assert np.allclose(oracle.flatten_params(m), z["flat_final"], rtol=1e-4, atol=1e-6)

@@ -32,10 +32,11 @@ def test_library_matches_golden(pkg, case):
     model = pkg.Chain(widths, not ident).load_flat(z["flat0"])
     opt = pkg.AdamRegularized() if str(z["opt"]) == "adam" else pkg.NesterovRegularized()
     tk = str(z["target"])
-    tobj = {"shiftscale": pkg.TransformShiftscale, "isa": pkg.TransformISA, "pinv": pkg.TransformPseudoInv}[tk]()
+    topts = {str(k): False for k in z["topts"]}
+    tobj = {"shiftscale": pkg.TransformShiftscale, "isa": pkg.TransformISA, "pinv": pkg.TransformPseudoInv}[tk](**topts)
     iso = pkg.Iso(data, opt=opt, model=model, target=tobj, minibatch=B)
-    assert np.allclose(rec(pkg.chis(iso)), z["chi0"], rtol=1e-4, atol=1e-5)
-    assert np.allclose(rec(pkg.koopman(iso)), z["kchi0"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(rec(pkg.chis(iso)), z["chi0"], rtol=1e-4, atol=5e-5)       # 1e-4 on chi
+    assert np.allclose(rec(pkg.koopman(iso)), z["kchi0"], rtol=1e-4, atol=5e-5)
     tol_t = 2e-4 if tk == "shiftscale" else 2e-3 * np.abs(z["target0"]).max()
     assert np.allclose(rec(pkg.isotarget(iso)), z["target0"], atol=tol_t)
     pkg.run_(iso, n_iter, perms=z["perms"])
