@@ -682,6 +682,18 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
   const int L = c.L, d = c.d;
   if (Bloc == 0) {
     IK_CUDA(cudaMemsetAsync(c.grads.p, 0, (size_t)(c.P + 4) * sizeof(float), c.stream));
+  } else if (c.fused_train && Bloc <= 8192) {
+    // narrow net, small minibatch: featurize -> one fused forward/loss/backward kernel -> ordered reduce
+    ensure_act(c, Bloc);
+    ensure_folded(c);
+    const bool pairs = c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
+    launch_featurize(c, c.xs, c.perm_dev.p, s0, Bloc, pairs, c.ln, c.act[0].p, c.F);
+    launch_narrow_train(c, c.act[0].p, Bloc, c.perm_dev.p + s0, (double)len, layer_segment(c, 0),
+                        c.ln ? c.gfold.p : c.grads.p + c.off_w[0]);
+    if (c.ln)
+      launch_unfold_ln(c, c.params.p + c.off_gamma, c.params.p + c.off_beta, c.params.p + c.off_w[0], c.gfold.p, c.F,
+                       c.cfg.widths[1], c.grads.p + c.off_gamma, c.grads.p + c.off_beta, c.grads.p + c.off_w[0],
+                       c.grads.p + c.off_b[0]);
   } else {
     forward_rows(c, c.xs, c.perm_dev.p, s0, Bloc, true, true);
     c.delta_a.ensure((size_t)Bloc * c.maxw);
@@ -946,6 +958,7 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
                  "ISOKANN_GEMM_TC needs >= 2 layers, hidden widths >= 256, input width >= 64, output <= 8");
     c->tc = cfg->gemm_mode != ISOKANN_GEMM_FP32 && tc_eligible(*cfg);
     c->tcn = !c->tc && cfg->gemm_mode == ISOKANN_GEMM_AUTO && tcn_eligible(*cfg);
+    c->fused_train = !c->tc && cfg->gemm_mode == ISOKANN_GEMM_AUTO && narrow_train_eligible(*cfg);
     if (c->tc || c->tcn) {
       c->tcs = new TcState;
       c->tcs->act.resize(c->L);

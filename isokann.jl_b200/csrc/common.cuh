@@ -134,6 +134,9 @@ void launch_fold_ln(Ctx &c, const float *gamma, const float *beta, const float *
 void launch_unfold_ln(Ctx &c, const float *gamma, const float *beta, const float *W1, const float *gfold, int F,
                       int h1, float *g_gamma, float *g_beta, float *g_W1, float *g_b1);
 void launch_optimiser(Ctx &c, int64_t P, float bt1, float bt2);
+bool narrow_train_eligible(const isokann_config &g);
+void launch_narrow_train(Ctx &c, const float *xhat, int64_t Bloc, const int64_t *idx, double Bglobal,
+                         const float *seg0, float *g0);
 void launch_perm_to_zero_based(Ctx &c, const int64_t *perm1, int64_t n, int64_t *out0);
 void launch_compact_gather(Ctx &c, const float *padded, int world, int64_t nmax, int64_t N, int d, float *out);
 
@@ -173,6 +176,7 @@ struct Ctx {
   float beta_t[2] = {0.f, 0.f};
   bool folded_valid = false;  // folded1 matches the current parameters
   bool tc = false;            // wide Dense layers run on tcgen05 (3xBF16 split)
+  bool fused_train = false;   // narrow net + small minibatch: one fused fwd/loss/bwd kernel per step
   bool tcn = false;           // narrow net: inference forward = one tcgen05 GEMM with the MLP tail in its epilogue
   bool tc_weights_valid = false;
   TcState *tcs = nullptr;

@@ -1,0 +1,344 @@
+// Fused forward + loss + backward for narrow nets (default pairnets: F -> h1 <= 128 -> <= 16 ... -> d)
+// on small minibatches -- the strictly sequential regime of train_batch! (reference
+// src/iso.jl:179-194: floor(N/B) dependent steps, default B = 100, scripts use 1000).
+//
+// The reference pays ~4 broadcast kernels x 8 parameter arrays + 2 gathers + fwd/bwd GEMM launches
+// per step; the generic path of this library still needed ~17 launches of latency-bound GEMMs
+// (~0.6 ms per step at B = 1000).  Here one kernel does everything between the featurizer and the
+// optimiser for a slice of 16 minibatch rows per CTA:
+//   x_hat rows -> shared memory (transposed, 16 rows per feature) -> layer 1 (thread = output
+//   column, 8 rows in registers, weights streamed coalesced from L2) -> tail layers -> loss and
+//   delta -> backward through the tail -> layer-1 weight gradient as 16-row outer products.
+// Every CTA writes its gradient partial (folded layout [W1'; b1'] | [W2; b2] | ...) to a private
+// slice; narrow_reduce_kernel adds the slices in CTA order, so the result is deterministic.
+#include "common.cuh"
+
+namespace ik {
+
+namespace {
+
+constexpr int R = 16;          // minibatch rows per group
+constexpr int H1P = 128;       // padded first hidden width
+constexpr int TW = 16;         // padded tail width
+constexpr int NT = 256;
+
+struct NarrowP {
+  const float *xhat;
+  int64_t ldx;
+  int B, F, L;
+  int w[ISOKANN_MAX_LAYERS + 1];
+  const float *seg[ISOKANN_MAX_LAYERS];
+  int64_t off[ISOKANN_MAX_LAYERS + 1];  // offsets of the layers inside one partial
+  const float *target;
+  const int64_t *idx;
+  const float *wloss;
+  double Bglobal;
+  int act, last_act;
+  float *part;
+  int64_t part_stride;
+  double *part_loss;
+  int groups;
+};
+
+__device__ __forceinline__ float actf(float a, int kind) {
+  switch (kind) {
+    case ISOKANN_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-a));
+    case ISOKANN_ACT_TANH: return tanhf(a);
+    case ISOKANN_ACT_RELU: return fmaxf(a, 0.f);
+    default: return a;
+  }
+}
+__device__ __forceinline__ float dactf(float z, int kind) {
+  switch (kind) {
+    case ISOKANN_ACT_SIGMOID: return z * (1.0f - z);
+    case ISOKANN_ACT_TANH: return 1.0f - z * z;
+    case ISOKANN_ACT_RELU: return z > 0.f ? 1.0f : 0.f;
+    default: return 1.0f;
+  }
+}
+
+__global__ void __launch_bounds__(NT) narrow_fwd_bwd_kernel(NarrowP p) {
+  extern __shared__ __align__(16) float sm[];
+  float *xT = sm;                                 // [F][R]
+  float *z1 = xT + (size_t)p.F * R;               // [R][H1P]
+  float *d1 = z1 + R * H1P;                       // [R][H1P]
+  float *zt = d1 + R * H1P;                       // [L-1][R][TW]  activations of layers 2..L
+  float *dt = zt + (ISOKANN_MAX_LAYERS)*R * TW;   // [L-1][R][TW]  deltas of layers 2..L
+  __shared__ double red[NT / 32];
+  const int tid = threadIdx.x;
+  const int h1 = p.w[1];
+  const int L = p.L;
+  float *part = p.part + (int64_t)blockIdx.x * p.part_stride;
+  double loss_acc = 0.0;
+  bool first = true;
+
+  for (int g = blockIdx.x; g < p.groups; g += gridDim.x) {
+    const int row0 = g * R;
+    __syncthreads();
+    // (1) x_hat rows of this group, transposed: xT[k][r]
+    for (int e = tid; e < R * p.F; e += NT) {
+      const int r = e & (R - 1), k = e >> 4;
+      const int row = row0 + r;
+      xT[e] = row < p.B ? __ldg(p.xhat + (int64_t)row * p.ldx + k) : 0.f;
+    }
+    __syncthreads();
+    // (2) layer 1: thread = (column j, k half); 16 rows in registers, the two k halves are combined
+    //     through shared memory (d1 is free during the forward pass)
+    {
+      const int j = tid & (H1P - 1), kh = tid >> 7;
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+      if (j < h1) {
+        const int kmid = (p.F + 1) / 2;
+        const int k0 = kh ? kmid : 0, k1 = kh ? p.F : kmid;
+        const float *wcol = p.seg[0] + j;
+        const float4 *x4 = reinterpret_cast<const float4 *>(xT);
+        // weights are streamed from L2: issue PF loads before any dependent FMA (the first ncu capture showed
+        // the compiler serialising load -> use, 8 exposed L2 round trips per unrolled body)
+        constexpr int PF = 16;
+        for (int kb = k0; kb < k1; kb += PF) {
+          float wv[PF];
+#pragma unroll
+          for (int u = 0; u < PF; ++u) wv[u] = kb + u < k1 ? __ldg(wcol + (int64_t)(kb + u) * h1) : 0.f;
+#pragma unroll
+          for (int u = 0; u < PF; ++u) {
+            const int k = min(kb + u, k1 - 1);
+            const float4 a = x4[k * 4], b = x4[k * 4 + 1], c = x4[k * 4 + 2], e = x4[k * 4 + 3];
+            const float w = wv[u];
+            acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]);
+            acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
+            acc[4] = fmaf(b.x, w, acc[4]); acc[5] = fmaf(b.y, w, acc[5]);
+            acc[6] = fmaf(b.z, w, acc[6]); acc[7] = fmaf(b.w, w, acc[7]);
+            acc[8] = fmaf(c.x, w, acc[8]); acc[9] = fmaf(c.y, w, acc[9]);
+            acc[10] = fmaf(c.z, w, acc[10]); acc[11] = fmaf(c.w, w, acc[11]);
+            acc[12] = fmaf(e.x, w, acc[12]); acc[13] = fmaf(e.y, w, acc[13]);
+            acc[14] = fmaf(e.z, w, acc[14]); acc[15] = fmaf(e.w, w, acc[15]);
+          }
+        }
+        if (kh) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) d1[r * H1P + j] = acc[r];
+        }
+      }
+      __syncthreads();
+      if (j < h1 && !kh) {
+        const float b = __ldg(p.seg[0] + (int64_t)p.F * h1 + j);
+        const int kind = L == 1 ? p.last_act : p.act;
+#pragma unroll
+        for (int r = 0; r < R; ++r) z1[r * H1P + j] = actf(acc[r] + d1[r * H1P + j] + b, kind);
+      }
+    }
+    __syncthreads();
+    // (3) tail layers l = 2..L (layer l: w[l-1] -> w[l])
+    for (int l = 2; l <= L; ++l) {
+      const int win = p.w[l - 1], wout = p.w[l];
+      const float *in = l == 2 ? z1 : zt + (l - 3) * R * TW;
+      const int ldin = l == 2 ? H1P : TW;
+      float *out = zt + (l - 2) * R * TW;
+      const float *sg = p.seg[l - 1];
+      if (tid < R * wout) {
+        const int r = tid / wout, j = tid - r * wout;
+        float acc = __ldg(sg + win * wout + j);
+        for (int k = 0; k < win; ++k) acc = fmaf(in[r * ldin + k], __ldg(sg + k * wout + j), acc);
+        out[r * TW + j] = actf(acc, l == L ? p.last_act : p.act);
+      }
+      __syncthreads();
+    }
+    // (4) loss and delta of the last layer
+    {
+      const int d = p.w[L];
+      const float *chi = L == 1 ? z1 : zt + (L - 2) * R * TW;
+      const int ldc = L == 1 ? H1P : TW;
+      float *dl = L == 1 ? d1 : dt + (L - 2) * R * TW;
+      double l = 0.0;
+      if (tid < R * d) {
+        const int r = tid / d, a = tid - r * d;
+        const int row = row0 + r;
+        float delta = 0.f;
+        if (row < p.B) {
+          const float c = chi[r * ldc + a];
+          const float y = __ldg(p.target + p.idx[row] * d + a);
+          const float res = c - y;
+          if (d == 1) {
+            l = (double)res * (double)res;
+            delta = (float)(2.0 * (double)res / p.Bglobal);
+          } else {
+            const float wa = __ldg(p.wloss + a);
+            const float z = res * wa;
+            l = (double)(z * z);
+            delta = ((2.0f * z) * (float)(1.0 / p.Bglobal)) * wa;
+          }
+          delta *= dactf(c, p.last_act);
+        }
+        dl[r * ldc + a] = delta;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+      if ((tid & 31) == 0) red[tid >> 5] = l;
+      __syncthreads();
+      if (tid == 0) {
+        double s = 0.0;
+        for (int k = 0; k < NT / 32; ++k) s += red[k];
+        loss_acc += s;
+      }
+    }
+    // (5) backward through the tail layers l = L..2
+    for (int l = L; l >= 2; --l) {
+      const int win = p.w[l - 1], wout = p.w[l];
+      const float *in = l == 2 ? z1 : zt + (l - 3) * R * TW;
+      const int ldin = l == 2 ? H1P : TW;
+      const float *dl = dt + (l - 2) * R * TW;
+      float *dprev = l == 2 ? d1 : dt + (l - 3) * R * TW;
+      const float *sg = p.seg[l - 1];
+      float *gp = part + p.off[l - 1];
+      for (int o = tid; o < (win + 1) * wout; o += NT) {
+        const int k = o / wout, j = o - k * wout;
+        float s = 0.f;
+        if (k < win) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) s = fmaf(in[r * ldin + k], dl[r * TW + j], s);
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) s += dl[r * TW + j];
+        }
+        gp[o] = first ? s : gp[o] + s;
+      }
+      for (int o = tid; o < R * win; o += NT) {
+        const int r = o / win, k = o - r * win;
+        float s = 0.f;
+        for (int j = 0; j < wout; ++j) s = fmaf(dl[r * TW + j], __ldg(sg + k * wout + j), s);
+        dprev[r * ldin + k] = s * dactf(in[r * ldin + k], p.act);
+      }
+      __syncthreads();
+    }
+    // (6) layer-1 gradient [(F+1) x h1] = [x_hat, 1]^T * delta_1 over this group's 16 rows
+    {
+      const int j = tid & (H1P - 1), half = tid >> 7;
+      if (j < h1) {
+        float dc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) dc[r] = d1[r * H1P + j];
+        const int kh = (p.F + 2) / 2;
+        const int k0 = half * kh, k1 = min(p.F + 1, k0 + kh);
+        const float4 *x4 = reinterpret_cast<const float4 *>(xT);
+        float *gp = part + j;
+#pragma unroll 2
+        for (int k = k0; k < k1; ++k) {
+          float s = 0.f;
+          if (k < p.F) {
+            const float4 a = x4[k * 4], b = x4[k * 4 + 1], c = x4[k * 4 + 2], e = x4[k * 4 + 3];
+            s = fmaf(a.x, dc[0], s); s = fmaf(a.y, dc[1], s); s = fmaf(a.z, dc[2], s); s = fmaf(a.w, dc[3], s);
+            s = fmaf(b.x, dc[4], s); s = fmaf(b.y, dc[5], s); s = fmaf(b.z, dc[6], s); s = fmaf(b.w, dc[7], s);
+            s = fmaf(c.x, dc[8], s); s = fmaf(c.y, dc[9], s); s = fmaf(c.z, dc[10], s); s = fmaf(c.w, dc[11], s);
+            s = fmaf(e.x, dc[12], s); s = fmaf(e.y, dc[13], s); s = fmaf(e.z, dc[14], s); s = fmaf(e.w, dc[15], s);
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) s += dc[r];
+          }
+          const int64_t o = (int64_t)k * h1;
+          gp[o] = first ? s : gp[o] + s;
+        }
+      }
+    }
+    first = false;
+  }
+  if (tid == 0) p.part_loss[blockIdx.x] = loss_acc;
+}
+
+struct ReduceP {
+  const float *part;
+  int64_t part_stride;
+  int nparts;
+  int nseg;
+  int64_t off[ISOKANN_MAX_LAYERS + 1];
+  float *dest[ISOKANN_MAX_LAYERS];
+  const double *part_loss;
+  float *packed_tail;
+};
+
+__global__ void narrow_reduce_kernel(ReduceP p) {
+  const int64_t total = p.off[p.nseg];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = p.part[i];
+    for (int c = 1; c < p.nparts; ++c) s += p.part[(int64_t)c * p.part_stride + i];
+    int sgi = 0;
+    while (i >= p.off[sgi + 1]) ++sgi;
+    p.dest[sgi][i - p.off[sgi]] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double l = 0.0;
+    for (int c = 0; c < p.nparts; ++c) l += p.part_loss[c];
+    const float hi = (float)l;
+    p.packed_tail[0] = hi;
+    p.packed_tail[1] = (hi == hi && fabsf(hi) != INFINITY) ? (float)(l - (double)hi) : 0.f;
+  }
+}
+
+}  // namespace
+
+bool narrow_train_eligible(const isokann_config &g) {
+  if (g.n_layers < 1 || g.n_layers > 4) return false;
+  if (g.widths[1] > H1P) return false;
+  for (int l = 2; l <= g.n_layers; ++l)
+    if (g.widths[l] > TW) return false;
+  if (g.widths[g.n_layers] > kMaxD) return false;
+  // x_hat tile + activations must fit shared memory
+  const size_t smem = ((size_t)g.widths[0] * R + 2 * R * H1P + 2 * ISOKANN_MAX_LAYERS * R * TW) * sizeof(float);
+  return smem <= 200 * 1024;
+}
+
+// xhat: [Bloc x F] normalised features of the minibatch slice (row-major); writes the gradient of the folded
+// first segment to g0 ((F+1) x h1) and of the tail layers to gtail[l-1], and the packed step loss
+void launch_narrow_train(Ctx &c, const float *xhat, int64_t Bloc, const int64_t *idx, double Bglobal,
+                         const float *seg0, float *g0) {
+  const int F = c.F, L = c.L;
+  NarrowP p{};
+  p.xhat = xhat; p.ldx = F; p.B = (int)Bloc; p.F = F; p.L = L;
+  for (int l = 0; l <= L; ++l) p.w[l] = c.cfg.widths[l];
+  p.seg[0] = seg0;
+  for (int l = 1; l < L; ++l) p.seg[l] = c.params.p + c.off_w[l];
+  int64_t off = 0;
+  for (int l = 0; l < L; ++l) {
+    p.off[l] = off;
+    off += (int64_t)(c.cfg.widths[l] + 1) * c.cfg.widths[l + 1];
+  }
+  p.off[L] = off;
+  p.target = c.target.p; p.idx = idx; p.wloss = c.w_loss.p; p.Bglobal = Bglobal;
+  p.act = c.cfg.activation; p.last_act = c.cfg.last_activation;
+  p.groups = cdiv(Bloc, R);
+  const int nparts = std::min(p.groups, 2 * c.num_sms);
+  const int64_t stride = (off + 3) & ~(int64_t)3;
+  c.splitk.ensure((size_t)nparts * stride);
+  c.red_d.ensure((size_t)std::max(nparts, 1024));
+  p.part = c.splitk.p; p.part_stride = stride; p.part_loss = c.red_d.p;
+  const size_t smem = ((size_t)F * R + 2 * R * H1P + 2 * ISOKANN_MAX_LAYERS * R * TW) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    IK_CUDA(cudaFuncSetAttribute(narrow_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  c.timer.begin(KC_GEMM, c.stream);
+  narrow_fwd_bwd_kernel<<<nparts, NT, smem, c.stream>>>(p);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  double macs = 0;
+  for (int l = 0; l < L; ++l) macs += (double)c.cfg.widths[l] * c.cfg.widths[l + 1];
+  c.count_launch(KC_GEMM, 6.0 * macs * (double)Bloc);
+
+  ReduceP r{};
+  r.part = c.splitk.p; r.part_stride = stride; r.nparts = nparts; r.nseg = L;
+  for (int l = 0; l <= L; ++l) r.off[l] = p.off[l];
+  r.dest[0] = g0;
+  for (int l = 1; l < L; ++l) r.dest[l] = c.grads.p + c.off_w[l];
+  r.part_loss = c.red_d.p;
+  r.packed_tail = c.grads.p + c.P;
+  int grid = (int)std::min<int64_t>((off + 255) / 256, (int64_t)c.num_sms * 4);
+  c.timer.begin(KC_REDUCE, c.stream);
+  narrow_reduce_kernel<<<grid, 256, 0, c.stream>>>(r);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_REDUCE);
+}
+
+}  // namespace ik

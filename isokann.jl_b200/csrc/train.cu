@@ -100,15 +100,17 @@ __global__ void fold_ln_kernel(const float *__restrict__ gamma, const float *__r
                                const float *__restrict__ W1, const float *__restrict__ b1, int F, int h1,
                                float *__restrict__ folded) {
   const int64_t total = (int64_t)F * h1;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int f = (int)(t / h1);
-    folded[t] = gamma[f] * W1[t];
-    if (f == 0) {
-      const int j = (int)t;
-      float s = b1[j];
-      for (int g = 0; g < F; ++g) s = fmaf(beta[g], W1[(int64_t)g * h1 + j], s);
-      folded[total + j] = s;
-    }
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+    folded[t] = gamma[t / h1] * W1[t];
+  // bias row: one warp per output column j, lanes stride over the input features
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < h1; j += gridDim.x * wpb) {
+    float s = 0.f;
+    for (int g = lane; g < F; g += 32) s = fmaf(beta[g], W1[(int64_t)g * h1 + j], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) folded[total + j] = b1[j] + s;
   }
 }
 

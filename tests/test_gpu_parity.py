@@ -317,4 +317,4 @@ def test_full_size_c3_iteration_properties(pkg, oracle):
     assert len(iso.losses) == 2 and np.isfinite(iso.losses).all()
     assert iso.losses[1] < iso.losses[0] * 1.5
     st = iso.engine.stats()
-    assert st["kernel_launches"] > 2 * (N // 1000) * 8
+    assert st["kernel_launches"] > 2 * (N // 1000) * 3
