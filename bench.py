@@ -317,10 +317,7 @@ def run_b200(args, pkg):
 
         def e2e_step(i):
             # SimulationData upload + run!(iso, 1) + chis(iso) back on the host
-            if world > 1:
-                eng.set_data(xs_j, ys_j, n_offset=off, n_local=n_loc)
-            else:
-                eng.set_data(xs_j, ys_j)
+            eng.set_data_async(xs_j, ys_j, n_offset=off, n_local=n_loc)
             eng.iterate(w.target, 1, 1, B, perms[i % len(perms)], **opts)
             eng._check(eng.lib.isokann_chis(eng.h, L.ptr(chi_host)))
         for i in range(2):
@@ -330,7 +327,7 @@ def run_b200(args, pkg):
         d2h = 8 + 4 * N * model.widths[-1]
         e2e = {"value": N * K * nsteps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / nsteps,
-               "call": "SimulationData upload (pinned host xs, ys) + run!(iso,1) + chis(iso) to host"}
+               "call": "isokann_set_data_async (pinned host xs, ys; ys streamed behind the Koopman pass) + run!(iso,1) + chis(iso) to host"}
         eng.set_data_dev(xs, ys, w.D, K, N, off, n_loc)
 
     if rank != 0:

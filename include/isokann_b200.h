@@ -138,6 +138,13 @@ int32_t isokann_set_data_f64(isokann_ctx *ctx, const double *xs, const double *y
  * [n_offset, n_offset+n_local) of this rank only. */
 int32_t isokann_set_data_sharded(isokann_ctx *ctx, const float *xs, const float *ys_local, int64_t D, int64_t K,
                                  int64_t N, int64_t n_offset, int64_t n_local);
+/* Asynchronous form of isokann_set_data_sharded: xs is copied before the call returns, ys_local is streamed
+ * to the device on a second CUDA stream and the next Koopman pass (isokann_koopman / isokann_target /
+ * isokann_iterate) consumes it chunk by chunk as it arrives, so the PCIe transfer overlaps the compute.
+ * ys_local should be page-locked and must stay valid and unmodified until that pass (or
+ * isokann_synchronize) has returned. */
+int32_t isokann_set_data_async(isokann_ctx *ctx, const float *xs, const float *ys_local, int64_t D, int64_t K,
+                               int64_t N, int64_t n_offset, int64_t n_local);
 /* Same with buffers already resident on this context's device (no copy of ys: it is adopted by
  * reference and must stay alive until the next set_data / destroy). */
 int32_t isokann_set_data_dev(isokann_ctx *ctx, const float *dev_xs, const float *dev_ys_local, int64_t D, int64_t K,

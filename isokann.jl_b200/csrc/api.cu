@@ -155,6 +155,11 @@ void forward_rows(Ctx &c, const float *in, const int64_t *gather, int64_t goff, 
     forward_rows_tcn(c, in, gather, goff, M, in_is_coords);
     return;
   }
+  if (c.tiny && !keep && gather == nullptr) {
+    c.act[c.L].ensure((size_t)M * c.d);
+    launch_tiny_forward(c, in, M, c.act[c.L].p);
+    return;
+  }
   ensure_act(c, M);
   ensure_folded(c);
   const bool pairs = in_is_coords && c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
@@ -405,11 +410,16 @@ void compute_koopman(Ctx &c) {
   const int64_t nsp = ch / c.K;
   for (int64_t n0 = 0; n0 < c.n_loc; n0 += nsp) {
     const int64_t ns = std::min(nsp, c.n_loc - n0);
+    if (c.ys_chunk_pts > 0) {  // ys is still streaming in (isokann_set_data_async): wait for the covering chunk
+      const int64_t last = std::min<int64_t>((n0 + ns - 1) / c.ys_chunk_pts, c.ys_chunks_pending - 1);
+      IK_CUDA(cudaStreamWaitEvent(c.stream, c.ys_events[(size_t)last], 0));
+    }
     forward_rows(c, c.ys + n0 * c.K * c.D, nullptr, 0, ns * c.K, true);
     launch_kmean(c, c.act[c.L].p, c.has_weights ? c.kweights.p + n0 * c.K : nullptr, ns, (int)c.K, c.d,
                  dst + n0 * c.d);
   }
   if (c.world > 1) allgather_rows(c, c.kchi_loc.p, c.n_loc, c.kchi.p);
+  c.ys_chunk_pts = 0;  // the whole upload has been waited for on this stream
   c.timer.end(c.stream);
 }
 
@@ -807,7 +817,11 @@ void upload_rows(Ctx &c, const void *host, bool f64, int64_t count, float *dev) 
 }
 
 void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_ptrs, int64_t D, int64_t K, int64_t N,
-                   int64_t n_off, int64_t n_loc) {
+                   int64_t n_off, int64_t n_loc, bool async_ys = false) {
+  if (c.ys_chunk_pts > 0) {  // a previous asynchronous upload may still be running
+    IK_CUDA(cudaStreamSynchronize(c.copy_stream));
+    c.ys_chunk_pts = 0;
+  }
   IK_REQUIRE(xs != nullptr, ISOKANN_BAD_ARGUMENT, "xs must not be NULL");
   IK_REQUIRE(D == c.D, ISOKANN_BAD_ARGUMENT, "coordinate dimension does not match the featurizer/model");
   IK_REQUIRE(N > 0 && K >= 0, ISOKANN_BAD_ARGUMENT, "N must be positive");
@@ -828,7 +842,29 @@ void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_pt
     c.ys = nullptr;
     if (ys && K > 0 && n_loc > 0) {
       c.ys_own.ensure((size_t)n_loc * K * D);
-      upload_rows(c, ys, f64, n_loc * K * D, c.ys_own.p);
+      if (async_ys && !f64) {
+        // stream ys in on a second stream, ~64 MiB per chunk, one event per chunk; the Koopman pass waits per
+        // chunk, so the PCIe transfer overlaps the forward pass over the chunks that already arrived
+        if (!c.copy_stream) IK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        const int64_t pts = std::max<int64_t>(1, (64ll << 20) / (K * D * 4));
+        const int64_t nchunks = (n_loc + pts - 1) / pts;
+        while ((int64_t)c.ys_events.size() < nchunks) {
+          cudaEvent_t e;
+          IK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          c.ys_events.push_back(e);
+        }
+        const float *src = (const float *)ys;
+        for (int64_t i = 0; i < nchunks; ++i) {
+          const int64_t p0 = i * pts, np = std::min(pts, n_loc - p0);
+          IK_CUDA(cudaMemcpyAsync(c.ys_own.p + p0 * K * D, src + p0 * K * D, (size_t)np * K * D * sizeof(float),
+                                  cudaMemcpyHostToDevice, c.copy_stream));
+          IK_CUDA(cudaEventRecord(c.ys_events[(size_t)i], c.copy_stream));
+        }
+        c.ys_chunk_pts = pts;
+        c.ys_chunks_pending = nchunks;
+      } else {
+        upload_rows(c, ys, f64, n_loc * K * D, c.ys_own.p);
+      }
       c.ys = c.ys_own.p;
     }
   }
@@ -959,6 +995,7 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
     c->tc = cfg->gemm_mode != ISOKANN_GEMM_FP32 && tc_eligible(*cfg);
     c->tcn = !c->tc && cfg->gemm_mode == ISOKANN_GEMM_AUTO && tcn_eligible(*cfg);
     c->fused_train = !c->tc && cfg->gemm_mode == ISOKANN_GEMM_AUTO && narrow_train_eligible(*cfg);
+    c->tiny = cfg->gemm_mode == ISOKANN_GEMM_AUTO && tiny_forward_eligible(*cfg);
     if (c->tc || c->tcn) {
       c->tcs = new TcState;
       c->tcs->act.resize(c->L);
@@ -1021,6 +1058,11 @@ int32_t isokann_destroy(isokann_ctx *c) {
   c->perm_raw.release();
   c->flags.release();
   c->ticket.release();
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+  }
+  for (auto e : c->ys_events) cudaEventDestroy(e);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1081,6 +1123,11 @@ int32_t isokann_set_data_f64(isokann_ctx *c, const double *xs, const double *ys,
 int32_t isokann_set_data_sharded(isokann_ctx *c, const float *xs, const float *ys_local, int64_t D, int64_t K,
                                  int64_t N, int64_t n_offset, int64_t n_local) {
   return guarded(c, [&] { set_data_impl(*c, xs, ys_local, false, false, D, K, N, n_offset, n_local); });
+}
+
+int32_t isokann_set_data_async(isokann_ctx *c, const float *xs, const float *ys_local, int64_t D, int64_t K, int64_t N,
+                               int64_t n_offset, int64_t n_local) {
+  return guarded(c, [&] { set_data_impl(*c, xs, ys_local, false, false, D, K, N, n_offset, n_local, true); });
 }
 
 int32_t isokann_set_data_dev(isokann_ctx *c, const float *dev_xs, const float *dev_ys_local, int64_t D, int64_t K,
@@ -1303,7 +1350,10 @@ int32_t isokann_reset_stats(isokann_ctx *c) {
 }
 
 int32_t isokann_synchronize(isokann_ctx *c) {
-  return guarded(c, [&] { sync_stream(*c); });
+  return guarded(c, [&] {
+    if (c->copy_stream) IK_CUDA(cudaStreamSynchronize(c->copy_stream));
+    sync_stream(*c);
+  });
 }
 
 void *isokann_stream(isokann_ctx *c) { return c ? (void *)c->stream : nullptr; }

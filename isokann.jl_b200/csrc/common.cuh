@@ -135,6 +135,8 @@ void launch_unfold_ln(Ctx &c, const float *gamma, const float *beta, const float
                       int h1, float *g_gamma, float *g_beta, float *g_W1, float *g_b1);
 void launch_optimiser(Ctx &c, int64_t P, float bt1, float bt2);
 bool narrow_train_eligible(const isokann_config &g);
+bool tiny_forward_eligible(const isokann_config &g);
+void launch_tiny_forward(Ctx &c, const float *in, int64_t M, float *out);
 void launch_narrow_train(Ctx &c, const float *xhat, int64_t Bloc, const int64_t *idx, double Bglobal,
                          const float *seg0, float *g0);
 void launch_perm_to_zero_based(Ctx &c, const int64_t *perm1, int64_t n, int64_t *out0);
@@ -176,6 +178,7 @@ struct Ctx {
   float beta_t[2] = {0.f, 0.f};
   bool folded_valid = false;  // folded1 matches the current parameters
   bool tc = false;            // wide Dense layers run on tcgen05 (3xBF16 split)
+  bool tiny = false;          // every width <= 16, no featurizer/LayerNorm: thread-per-sample forward
   bool fused_train = false;   // narrow net + small minibatch: one fused fwd/loss/bwd kernel per step
   bool tcn = false;           // narrow net: inference forward = one tcgen05 GEMM with the MLP tail in its epilogue
   bool tc_weights_valid = false;
@@ -188,6 +191,11 @@ struct Ctx {
   const float *xs = nullptr, *ys = nullptr;
   int64_t N = 0, K = 0, n_off = 0, n_loc = 0;
   bool has_weights = false;
+  // asynchronous upload of ys (isokann_set_data_async): chunk i of ys is complete when ys_events[i] fires
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> ys_events;
+  int64_t ys_chunk_pts = 0;   // start points per upload chunk; 0 = no pending upload
+  int64_t ys_chunks_pending = 0;
   DevBuf<float> chi_x, kchi, kchi_loc, gather_pad, target, w_loss;
   bool has_target = false;
 

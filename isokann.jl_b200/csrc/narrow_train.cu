@@ -275,7 +275,92 @@ __global__ void narrow_reduce_kernel(ReduceP p) {
   }
 }
 
+// Forward pass of a tiny net (every width <= 16, e.g. smallnet [2,8,8,8,1] of the Langevin toy systems,
+// reference src/models.jl:102-108): one thread per sample, all [W; b] segments in shared memory,
+// activations in registers.  HBM traffic: 4*F bytes in, 4*d bytes out per sample.
+struct TinyP {
+  const float *in;      // [M x F] records (identity featurizer), optionally gathered
+  int64_t M;
+  int L;
+  int w[ISOKANN_MAX_LAYERS + 1];
+  const float *seg[ISOKANN_MAX_LAYERS];
+  int act, last_act;
+  float *out;           // [M x d]
+};
+
+__global__ void __launch_bounds__(256) tiny_forward_kernel(TinyP p) {
+  __shared__ float sw[ISOKANN_MAX_LAYERS * 17 * 16];
+  __shared__ int soff[ISOKANN_MAX_LAYERS + 1];
+  if (threadIdx.x == 0) {
+    int o = 0;
+    for (int l = 0; l < p.L; ++l) {
+      soff[l] = o;
+      o += (p.w[l] + 1) * p.w[l + 1];
+    }
+    soff[p.L] = o;
+  }
+  __syncthreads();
+  for (int l = 0; l < p.L; ++l) {
+    const int n = (p.w[l] + 1) * p.w[l + 1];
+    for (int e = threadIdx.x; e < n; e += blockDim.x) sw[soff[l] + e] = __ldg(p.seg[l] + e);
+  }
+  __syncthreads();
+  const int F = p.w[0];
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < p.M; m += (int64_t)gridDim.x * blockDim.x) {
+    float h[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) h[k] = k < F ? __ldg(p.in + m * F + k) : 0.f;
+    for (int l = 0; l < p.L; ++l) {
+      const int win = p.w[l], wout = p.w[l + 1];
+      const float *W = sw + soff[l];
+      float a[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = j < wout ? W[win * wout + j] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (k < win) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < wout) a[j] = fmaf(h[k], W[k * wout + j], a[j]);
+        }
+      }
+      const int kind = l == p.L - 1 ? p.last_act : p.act;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h[j] = j < wout ? actf(a[j], kind) : 0.f;
+    }
+    const int d = p.w[p.L];
+#pragma unroll
+    for (int j = 0; j < kMaxD; ++j)
+      if (j < d) p.out[m * d + j] = h[j];
+  }
+}
+
 }  // namespace
+
+bool tiny_forward_eligible(const isokann_config &g) {
+  if (g.layernorm || g.featurizer != ISOKANN_FEAT_IDENTITY) return false;
+  for (int l = 0; l <= g.n_layers; ++l)
+    if (g.widths[l] > 16) return false;
+  return g.widths[g.n_layers] <= kMaxD;
+}
+
+void launch_tiny_forward(Ctx &c, const float *in, int64_t M, float *out) {
+  if (M <= 0) return;
+  TinyP p{};
+  p.in = in; p.M = M; p.L = c.L;
+  for (int l = 0; l <= c.L; ++l) p.w[l] = c.cfg.widths[l];
+  for (int l = 0; l < c.L; ++l) p.seg[l] = c.params.p + c.off_w[l];
+  p.act = c.cfg.activation; p.last_act = c.cfg.last_activation;
+  p.out = out;
+  int grid = (int)std::min<int64_t>((M + 255) / 256, (int64_t)c.num_sms * 8);
+  c.timer.begin(KC_GEMM, c.stream);
+  tiny_forward_kernel<<<grid, 256, 0, c.stream>>>(p);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  double macs = 0;
+  for (int l = 0; l < c.L; ++l) macs += (double)c.cfg.widths[l] * c.cfg.widths[l + 1];
+  c.count_launch(KC_GEMM, 2.0 * macs * (double)M);
+}
 
 bool narrow_train_eligible(const isokann_config &g) {
   if (g.n_layers < 1 || g.n_layers > 4) return false;

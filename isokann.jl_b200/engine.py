@@ -138,6 +138,18 @@ class Engine:
                 self._check(self.lib.isokann_set_data_sharded(self.h, L.ptr(xs), L.ptr(ys), D, K, N, n_offset, n_local))
         self.N, self.K = N, K
 
+    def set_data_async(self, xs, ys, n_offset: int = 0, n_local: Optional[int] = None):
+        """like set_data, but ys (float32, Fortran-ordered, ideally page-locked) is streamed in behind the
+        call and consumed chunk-wise by the next Koopman pass; the caller keeps ys alive until then"""
+        xs = julia_f32(xs, 2)
+        ys = julia_f32(ys, 3)
+        D, N = xs.shape
+        K = ys.shape[1]
+        n_local = ys.shape[2] if n_local is None else n_local
+        self._keep = [xs, ys]
+        self._check(self.lib.isokann_set_data_async(self.h, L.ptr(xs), L.ptr(ys), D, K, N, n_offset, n_local))
+        self.N, self.K = N, K
+
     def set_data_dev(self, dev_xs, dev_ys, D: int, K: int, N: int, n_offset: int = 0, n_local: Optional[int] = None):
         """device-resident float32 buffers (torch tensors or raw addresses), records layout."""
         n_local = N if n_local is None else n_local

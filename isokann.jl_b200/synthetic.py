@@ -129,7 +129,9 @@ WORKLOADS = {
     "c1": Workload("c1_adp_small", "allpairs", 22, [231, 38, 6, 1], True, 100, 5, "shiftscale", "nesterov", 100, 0),
     "c2": Workload("c2_triplewell", "identity", 0, [2, 8, 8, 8, 1], False, 100_000, 8, "shiftscale", "nesterov", 4096, 1),
     "c3": Workload("c3_villin", "allpairs", 35, [595, 71, 8, 1], True, 100_000, 8, "shiftscale", "nesterov", 1000, 2),
-    "c4": Workload("c4_adp_nd", "allpairs", 22, [231, 38, 6, 3], True, 1_000_000, 8, "pinv", "nesterov", 65536, 3, 3),
+    # (TransformPseudoInv with the default Nesterov rule diverges on this data under the reference's own
+    #  semantics -- the oracle raises the same "model collapsed" DomainError -- so the bench default is ISA + Adam)
+    "c4": Workload("c4_adp_nd", "allpairs", 22, [231, 38, 6, 3], True, 1_000_000, 8, "isa", "adam", 65536, 3, 3),
     "c5": Workload("c5_villin_wide", "allpairs", 35, [595, 2048, 2048, 1], True, 1_000_000, 16, "shiftscale", "adam",
                    65536, 4),
 }

@@ -318,3 +318,26 @@ def test_full_size_c3_iteration_properties(pkg, oracle):
     assert iso.losses[1] < iso.losses[0] * 1.5
     st = iso.engine.stats()
     assert st["kernel_launches"] > 2 * (N // 1000) * 3
+
+
+def test_async_upload_matches_blocking_upload(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c3"]
+    N, K = 30_000, 8                                    # several 64 MiB upload chunks
+    xs, ys = pkg.synthetic.make_data(w, N, K)
+    flat = oracle.flatten_params(oracle_model(oracle, w.widths, True, 5))
+    iso = make_iso(pkg, w, xs, ys, flat)
+    k0 = pkg.koopman(iso)
+    ys2 = np.asfortranarray(ys[:, :, ::-1])             # different data through the asynchronous path
+    iso.engine.set_data_async(xs, ys2)
+    k1 = pkg.koopman(iso)
+    assert np.array_equal(k1[:, ::-1], k0)
+    t = pkg.isotarget(iso)                              # target + training still work on the streamed data
+    assert t.min() == 0.0 and t.max() == 1.0
+
+
+def test_tiny_net_forward_kernel(pkg, oracle):
+    # smallnet [2,8,8,8,1] of the Langevin toy systems: thread-per-sample forward, fused training step
+    r = run_pair(pkg, oracle, "c2", N=5000, K=4, minibatch=500, n_iter=3, opt="adam")
+    assert np.allclose(r["chi0_lib"], r["chi0_ref"], rtol=TOL_CHI, atol=1e-5)
+    assert np.allclose(r["loss_lib"], r["loss_ref"], rtol=1e-3)
+    assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=1e-3, atol=1e-4)
