@@ -80,9 +80,9 @@ def test_tc_large_batch_split_k(pkg, oracle):
     assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=1e-3, atol=1e-3)
 
 
-@pytest.mark.parametrize("target,topts", [("pinv", {"eigenvecs": False}), ("isa", {})])
+@pytest.mark.parametrize("target,topts", [("pinv", {"eigenvecs": False, "permute": False}), ("isa", {})])
 def test_tc_nd_target_iteration(pkg, oracle, target, topts):
-    # (the Schur vectors of eigenvecs=True are rounding-sensitive, see DESIGN.md section 2: a 1e-7 change of Kinv
+    # (fixperm at a random initialisation is a near-tie and the Schur vectors of eigenvecs=True are rounding-sensitive, see DESIGN.md section 2: a 1e-7 change of Kinv
     #  may flip them, so multi-iteration comparisons across different arithmetic use the stable options)
     r = run_pair(pkg, oracle, "c4", N=400, K=3, minibatch=100, n_iter=2, opt="adam", target=target, gemm="tc",
                  widths=[231, 256, 256, 3], target_opts=topts)
