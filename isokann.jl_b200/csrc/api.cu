@@ -203,7 +203,11 @@ bool tcn_eligible(const isokann_config &g) {
 void tc_ensure_rows(Ctx &c, int64_t rows) {
   TcState &t = *c.tcs;
   if (rows > t.rows) {
-    for (int l = 0; l < (c.tcn ? 1 : c.L); ++l) t.act[l].ensure(rows, t.wp[l]);
+    for (int l = 0; l < (c.tcn ? 1 : c.L); ++l) {
+      t.act[l].ensure(rows, t.wp[l]);
+      // column w_l := 1 once; the GEMM epilogues never touch it when w_l is a multiple of 32 and rewrite it otherwise
+      if (l > 0) launch_set_ones_col(c, t.act[l].hi.p, t.act[l].lo.p, rows, t.wp[l], c.cfg.widths[l]);
+    }
     c.act[c.L].ensure((size_t)rows * c.d);
     t.rows = rows;
   }
@@ -253,6 +257,7 @@ void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t gof
       return;
     }
     g.epi = TC_EPI_BIAS_ACT_SPLIT;
+    g.ones_col = 1;
     g.out_hi = t.act[l + 1].hi.p; g.out_lo = t.act[l + 1].lo.p; g.ldo = t.wp[l + 1];
     launch_tc_gemm(c, g);
   }
@@ -292,8 +297,7 @@ void backward_tc(Ctx &c, int64_t Bloc) {
   const int64_t ldT = (Bloc + 7) & ~(int64_t)7;
   int wmax = 0;
   for (int l = 0; l < L; ++l) wmax = std::max(wmax, c.cfg.widths[l]);
-  t.actT.ensure(wmax + 1, ldT);
-  t.deltaT.ensure(wmax, ldT);
+  t.actT.ensure(c.cfg.widths[L - 1] + 1, ldT);
   int wpmax = 0;
   for (int l = 0; l < L; ++l) wpmax = std::max(wpmax, t.wp[l]);
   t.delta[0].ensure(Bloc, wpmax);
@@ -308,14 +312,13 @@ void backward_tc(Ctx &c, int64_t Bloc) {
   }
   for (int l = L - 2; l >= 0; --l) {
     const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
-    // weight + bias gradient: [(fin+1) x fout] = [act_l, 1]^T * delta_{l+1}
-    launch_transpose_split(c, t.act[l].hi.p, t.act[l].lo.p, Bloc, fin, t.wp[l], t.actT.hi.p, t.actT.lo.p, ldT, true);
-    launch_transpose_split(c, t.delta[cur].hi.p, t.delta[cur].lo.p, Bloc, fout, t.wp[l + 1], t.deltaT.hi.p,
-                           t.deltaT.lo.p, ldT, false);
+    // weight + bias gradient: [(fin+1) x fout] = [act_l, 1]^T * delta_{l+1}.  Both operands are consumed as stored
+    // (batch-major rows) through MN-major UMMA descriptors; column fin of act_l is the constant 1.
     float *dest = (l == 0 && c.ln) ? c.gfold.p : c.grads.p + c.off_w[l];
     TcGemm w{};
-    w.a_hi = t.actT.hi.p; w.a_lo = t.actT.lo.p; w.lda = ldT;
-    w.b_hi = t.deltaT.hi.p; w.b_lo = t.deltaT.lo.p; w.ldb = ldT;
+    w.mn_major = 1;
+    w.a_hi = t.act[l].hi.p; w.a_lo = t.act[l].lo.p; w.lda = t.wp[l];
+    w.b_hi = t.delta[cur].hi.p; w.b_lo = t.delta[cur].lo.p; w.ldb = t.wp[l + 1];
     w.M = fin + 1; w.N = fout; w.K = (int)Bloc;
     w.epi = TC_EPI_F32; w.act = ISOKANN_ACT_IDENTITY;
     w.ldc = fout;
@@ -1001,7 +1004,8 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
       c->tcs->act.resize(c->L);
       c->tcs->wF.resize(c->L);
       c->tcs->wD.resize(c->L);
-      for (int l = 0; l <= c->L; ++l) c->tcs->wp.push_back((cfg->widths[l] + 63) & ~63);
+      // padded row length: room for a constant-1 column behind the activations (bias column of the wgrad GEMM)
+      for (int l = 0; l <= c->L; ++l) c->tcs->wp.push_back((cfg->widths[l] + 1 + 63) & ~63);
     }
     c->beta_t[0] = cfg->beta1;
     c->beta_t[1] = cfg->beta2;

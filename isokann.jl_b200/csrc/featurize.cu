@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) featurize_ln_kernel(const float *__restri
     if (out_hi) {  // bf16 (hi, lo) split for the tensor-core path; pad columns [F, ldo) are zeroed
       __nv_bfloat16 *oh = out_hi + m * ldo, *ol = out_lo + m * ldo;
       for (int f = lane; f < (int)ldo; f += 32) {
-        const float v = f < F ? (sf[f] - mu) * rstd : 0.f;
+        const float v = f < F ? (sf[f] - mu) * rstd : (f == F ? 1.f : 0.f);  // column F = 1: bias column
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         oh[f] = h;
         ol[f] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -193,8 +193,9 @@ __global__ void __launch_bounds__(256, (NF <= 20 ? 3 : 2)) featurize_reg_kernel(
       for (int t = 0; t < NF; t += 2) {
         const int f = 2 * lane + 64 * (t >> 1);
         if (f < (int)ldo) {
-          const float x0 = f < F ? fmaf(v[t], scale, shift) : 0.f;
-          const float x1 = f + 1 < F ? fmaf(v[t + 1], scale, shift) : 0.f;
+          // column F carries the constant 1 that turns the weight-gradient GEMM into [x_hat, 1]^T * delta
+          const float x0 = f < F ? fmaf(v[t], scale, shift) : (f == F ? 1.f : 0.f);
+          const float x1 = f + 1 < F ? fmaf(v[t + 1], scale, shift) : (f + 1 == F ? 1.f : 0.f);
           const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
           const uint32_t hw = *reinterpret_cast<const uint32_t *>(&h2);
           const __nv_bfloat162 l2 =

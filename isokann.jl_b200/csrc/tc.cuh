@@ -24,6 +24,8 @@ struct TcGemm {
   const __nv_bfloat16 *b_hi, *b_lo;
   int64_t ldb;
   int M, N, K;
+  int mn_major;                       // 1: A is [K x M] and B is [K x N] in memory (M / N contiguous): weight gradients
+  int ones_col;                       // split epilogues: write 1.0 into column N (bias column of the next wgrad)
   int epi, act;
   const float *bias;                  // TC_EPI_BIAS_ACT_SPLIT
   __nv_bfloat16 *out_hi, *out_lo;     // split outputs
@@ -73,7 +75,9 @@ struct TcState {
 
 // featurizer + LayerNorm writing the split-bf16 A operand [M x ld] (pad columns zeroed)
 void launch_featurize_split(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M,
-                            bool pairs, bool do_ln, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld);
+                            bool pairs, bool do_ln, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld);  // column F := 1
+// set column `col` of a split matrix to (hi, lo) = (1, 0) for every row
+void launch_set_ones_col(Ctx &c, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t rows, int64_t ld, int col);
 // [rows x cols] split (ld_in) -> transposed [cols(+ones row) x ld_out] split; columns >= rows are zero
 void launch_transpose_split(Ctx &c, const __nv_bfloat16 *in_hi, const __nv_bfloat16 *in_lo, int64_t rows, int cols,
                             int64_t ld_in, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld_out,

@@ -233,6 +233,13 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const __nv_bfloat16 *__
   }
 }
 
+__global__ void set_ones_col_kernel(__nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t rows, int64_t ld, int col) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    hi[r * ld + col] = __float2bfloat16_rn(1.0f);
+    lo[r * ld + col] = __float2bfloat16_rn(0.0f);
+  }
+}
+
 __global__ void dot_finish_kernel(const float *__restrict__ partial, int64_t M, int slots, int d,
                                   const float *__restrict__ bias, int act, float *__restrict__ chi) {
   const int64_t total = M * d;
@@ -246,6 +253,14 @@ __global__ void dot_finish_kernel(const float *__restrict__ partial, int64_t M, 
 }
 
 }  // namespace
+
+void launch_set_ones_col(Ctx &c, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t rows, int64_t ld, int col) {
+  if (rows <= 0) return;
+  int grid = (int)std::min<int64_t>((rows + 255) / 256, (int64_t)c.num_sms * 4);
+  set_ones_col_kernel<<<grid, 256, 0, c.stream>>>(hi, lo, rows, ld, col);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_TRAIN_EW);
+}
 
 void launch_dot_finish(Ctx &c, const float *partial, int64_t M, int slots, int d, const float *bias, int act,
                        float *chi) {

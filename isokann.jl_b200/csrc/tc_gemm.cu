@@ -97,6 +97,17 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
   return d;
 }
+// MN-major, 128B-swizzled operand tile built from 64(MN) x 64(K) TMA boxes: 64 MN-elements (128 B) per
+// k row, 8-row k groups 1024 B apart (stride byte offset), next 64 MN-elements 8192 B apart (leading byte offset)
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -142,7 +153,7 @@ __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w &
 struct TcParams {
   int M, N, K;          // D is M x N, reduction length K (elements)
   int m_tiles, n_tiles, splits, kb_per_split, num_kb;
-  int epi, act;
+  int epi, act, mn_major, ones_col;
   const float *bias;    // [N] or nullptr
   __nv_bfloat16 *out_hi, *out_lo;  // split outputs, row-major, leading dimension ldo
   int64_t ldo;
@@ -226,10 +237,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
           const uint32_t sa = base + stage * STAGE_BYTES;
           const uint32_t full = bar_full + 8 * stage;
           mbar_arrive_expect_tx(full, STAGE_BYTES);
-          tma_load_2d(sa, &map_ah, full, kb * BK, mb * BM);
-          tma_load_2d(sa + A_TILE, &map_al, full, kb * BK, mb * BM);
-          tma_load_2d(sa + 2 * A_TILE, &map_bh, full, kb * BK, nb * BN);
-          tma_load_2d(sa + 2 * A_TILE + B_TILE, &map_bl, full, kb * BK, nb * BN);
+          if (!p.mn_major) {
+            tma_load_2d(sa, &map_ah, full, kb * BK, mb * BM);
+            tma_load_2d(sa + A_TILE, &map_al, full, kb * BK, mb * BM);
+            tma_load_2d(sa + 2 * A_TILE, &map_bh, full, kb * BK, nb * BN);
+            tma_load_2d(sa + 2 * A_TILE + B_TILE, &map_bl, full, kb * BK, nb * BN);
+          } else {  // boxes of 64 (M or N, contiguous) x 64 (k)
+#pragma unroll
+            for (int b = 0; b < BM / 64; ++b) {
+              tma_load_2d(sa + b * 8192, &map_ah, full, mb * BM + 64 * b, kb * BK);
+              tma_load_2d(sa + A_TILE + b * 8192, &map_al, full, mb * BM + 64 * b, kb * BK);
+            }
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b) {
+              tma_load_2d(sa + 2 * A_TILE + b * 8192, &map_bh, full, nb * BN + 64 * b, kb * BK);
+              tma_load_2d(sa + 2 * A_TILE + B_TILE + b * 8192, &map_bl, full, nb * BN + 64 * b, kb * BK);
+            }
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -241,7 +265,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      if (p.mn_major) idesc |= (1u << 15) | (1u << 16);  // A and B are MN-major
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -257,11 +282,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = base + stage * STAGE_BYTES;
-          const uint64_t dah = make_desc_sw128(sa), dal = make_desc_sw128(sa + A_TILE);
-          const uint64_t dbh = make_desc_sw128(sa + 2 * A_TILE), dbl = make_desc_sw128(sa + 2 * A_TILE + B_TILE);
+          const bool mn = p.mn_major != 0;
+          const uint64_t dah = mn ? make_desc_mn_sw128(sa) : make_desc_sw128(sa);
+          const uint64_t dal = mn ? make_desc_mn_sw128(sa + A_TILE) : make_desc_sw128(sa + A_TILE);
+          const uint64_t dbh = mn ? make_desc_mn_sw128(sa + 2 * A_TILE) : make_desc_sw128(sa + 2 * A_TILE);
+          const uint64_t dbl =
+              mn ? make_desc_mn_sw128(sa + 2 * A_TILE + B_TILE) : make_desc_sw128(sa + 2 * A_TILE + B_TILE);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 16 bf16 = 32 B inside the swizzle atom
+            // K-major: 16 bf16 = 32 B inside the swizzle atom; MN-major: 16 k rows = two 1024 B groups
+            const uint64_t adv = mn ? (uint64_t)((k * 2048) >> 4) : (uint64_t)((k * 32) >> 4);
             umma_f16(tmem_d, dah + adv, dbh + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             umma_f16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
             umma_f16(tmem_d, dal + adv, dbh + adv, idesc, 1u);
@@ -414,10 +444,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
           }
           continue;
         }
-        if (!full) {  // columns >= N inside the padded leading dimension are written as zeros
+        if (!full) {  // columns >= N inside the padded leading dimension: zeros, except the bias column N
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j >= p.N) v[j] = 0.f;
+            if (col0 + j >= p.N) v[j] = (p.ones_col && col0 + j == p.N) ? 1.f : 0.f;
         }
         uint32_t ph[16], pl[16];
 #pragma unroll
@@ -513,6 +543,20 @@ void make_map(CUtensorMap *m, const void *ptr, int64_t rows, int64_t cols, int64
   IK_REQUIRE(r == CUDA_SUCCESS, ISOKANN_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
 }
 
+// MN-major operand: memory is [k_extent][ld] with mn_extent contiguous elements per row; boxes 64 x 64
+void make_map_mn(CUtensorMap *m, const void *ptr, int64_t mn_extent, int64_t k_extent, int64_t ld) {
+  IK_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, ISOKANN_BAD_ARGUMENT,
+             "tensor-core operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  cuuint64_t dims[2] = {(cuuint64_t)mn_extent, (cuuint64_t)k_extent};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IK_REQUIRE(r == CUDA_SUCCESS, ISOKANN_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+}
+
 }  // namespace
 
 int launch_tc_gemm(Ctx &c, const TcGemm &g) {
@@ -527,10 +571,17 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
     attr = true;
   }
   alignas(64) CUtensorMap mah, mal, mbh, mbl;
-  make_map(&mah, g.a_hi, g.M, g.K, g.lda, BM);
-  make_map(&mal, g.a_lo, g.M, g.K, g.lda, BM);
-  make_map(&mbh, g.b_hi, g.N, g.K, g.ldb, BN);
-  make_map(&mbl, g.b_lo, g.N, g.K, g.ldb, BN);
+  if (g.mn_major) {
+    make_map_mn(&mah, g.a_hi, g.M, g.K, g.lda);
+    make_map_mn(&mal, g.a_lo, g.M, g.K, g.lda);
+    make_map_mn(&mbh, g.b_hi, g.N, g.K, g.ldb);
+    make_map_mn(&mbl, g.b_lo, g.N, g.K, g.ldb);
+  } else {
+    make_map(&mah, g.a_hi, g.M, g.K, g.lda, BM);
+    make_map(&mal, g.a_lo, g.M, g.K, g.lda, BM);
+    make_map(&mbh, g.b_hi, g.N, g.K, g.ldb, BN);
+    make_map(&mbl, g.b_lo, g.N, g.K, g.ldb, BN);
+  }
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.m_tiles = cdiv(g.M, BM);
@@ -541,7 +592,7 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   splits = std::min(splits, p.num_kb);
   p.kb_per_split = cdiv(p.num_kb, splits);
   p.splits = cdiv(p.num_kb, p.kb_per_split);
-  p.epi = g.epi; p.act = g.act;
+  p.epi = g.epi; p.act = g.act; p.mn_major = g.mn_major; p.ones_col = g.ones_col;
   p.bias = g.bias;
   p.out_hi = g.out_hi; p.out_lo = g.out_lo; p.ldo = g.ldo;
   p.out_f32 = g.out_f32; p.ldc = g.ldc;
