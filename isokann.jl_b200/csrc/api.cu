@@ -294,10 +294,6 @@ void forward_rows_tcn(Ctx &c, const float *in, const int64_t *gather, int64_t go
 void backward_tc(Ctx &c, int64_t Bloc) {
   TcState &t = *c.tcs;
   const int L = c.L, d = c.d;
-  const int64_t ldT = (Bloc + 7) & ~(int64_t)7;
-  int wmax = 0;
-  for (int l = 0; l < L; ++l) wmax = std::max(wmax, c.cfg.widths[l]);
-  t.actT.ensure(c.cfg.widths[L - 1] + 1, ldT);
   int wpmax = 0;
   for (int l = 0; l < L; ++l) wpmax = std::max(wpmax, t.wp[l]);
   t.delta[0].ensure(Bloc, wpmax);
@@ -305,8 +301,29 @@ void backward_tc(Ctx &c, int64_t Bloc) {
   int cur = 0;
   {  // last (thin) layer
     const int l = L - 1, fin = c.cfg.widths[l];
-    launch_transpose_split(c, t.act[l].hi.p, t.act[l].lo.p, Bloc, fin, t.wp[l], t.actT.hi.p, t.actT.lo.p, ldT, true);
-    launch_thin_wgrad(c, t.actT.hi.p, t.actT.lo.p, ldT, fin, Bloc, c.delta_a.p, d, c.grads.p + c.off_w[l]);
+    // thin weight gradient [(fin+1) x d] = [z, 1]^T * delta_L on the same MN-major GEMM (N padded by TMA zero fill)
+    t.dlast.ensure(Bloc, 64);
+    launch_f32_to_split(c, c.delta_a.p, Bloc, d, t.dlast.hi.p, t.dlast.lo.p, 64);
+    TcGemm w{};
+    w.mn_major = 1;
+    w.a_hi = t.act[l].hi.p; w.a_lo = t.act[l].lo.p; w.lda = t.wp[l];
+    w.b_hi = t.dlast.hi.p; w.b_lo = t.dlast.lo.p; w.ldb = 64;
+    w.M = fin + 1; w.N = d; w.K = (int)Bloc;
+    w.epi = TC_EPI_F32; w.act = ISOKANN_ACT_IDENTITY;
+    w.ldc = d;
+    const int tiles = cdiv(w.M, 128);
+    const int splits = std::max(1, std::min(c.num_sms / tiles, (int)(Bloc / 1024)));
+    if (splits > 1) {
+      c.splitk.ensure((size_t)splits * w.M * w.N);
+      w.out_f32 = c.splitk.p;
+      w.splits = splits;
+      const int used = launch_tc_gemm(c, w);
+      launch_splitk_reduce(c, c.splitk.p, used, (int64_t)w.M * w.N, c.grads.p + c.off_w[l]);
+    } else {
+      w.out_f32 = c.grads.p + c.off_w[l];
+      w.splits = 1;
+      launch_tc_gemm(c, w);
+    }
     launch_thin_dgrad(c, c.delta_a.p, Bloc, d, c.params.p + c.off_w[l], fin, t.act[l].hi.p, t.act[l].lo.p, t.wp[l],
                       c.cfg.activation, t.delta[cur].hi.p, t.delta[cur].lo.p, t.wp[l]);
   }
@@ -1052,6 +1069,7 @@ int32_t isokann_destroy(isokann_ctx *c) {
     c->tcs->delta[0].release();
     c->tcs->delta[1].release();
     c->tcs->dot_partial.release();
+    c->tcs->dlast.release();
     delete c->tcs;
   }
   c->pairs.release();

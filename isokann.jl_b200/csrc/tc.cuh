@@ -68,6 +68,7 @@ struct TcState {
   std::vector<SplitBuf> wD;    // dgrad operand of layer l   (l = 1..L-2): [w_l x wp_{l+1}]
   SplitBuf actT, deltaT;       // transposed activation (+ ones row) / delta of the current layer
   SplitBuf delta[2];           // row-major delta ping-pong
+  SplitBuf dlast;              // split copy of the last layer's delta (B x d, padded to 64 columns)
   DevBuf<float> dot_partial;   // fused last layer: partial chi per 128-column slot
   std::vector<int> wp;         // padded widths
   int64_t rows = 0, train_rows = 0;
@@ -76,6 +77,9 @@ struct TcState {
 // featurizer + LayerNorm writing the split-bf16 A operand [M x ld] (pad columns zeroed)
 void launch_featurize_split(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M,
                             bool pairs, bool do_ln, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld);  // column F := 1
+// fp32 [rows x cols] (dense) -> split bf16 [rows x ld], pad columns zeroed
+void launch_f32_to_split(Ctx &c, const float *in, int64_t rows, int cols, __nv_bfloat16 *hi, __nv_bfloat16 *lo,
+                         int64_t ld);
 // set column `col` of a split matrix to (hi, lo) = (1, 0) for every row
 void launch_set_ones_col(Ctx &c, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t rows, int64_t ld, int col);
 // [rows x cols] split (ld_in) -> transposed [cols(+ones row) x ld_out] split; columns >= rows are zero

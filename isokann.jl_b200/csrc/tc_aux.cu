@@ -233,6 +233,20 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const __nv_bfloat16 *__
   }
 }
 
+__global__ void f32_to_split_kernel(const float *__restrict__ in, int64_t rows, int cols, __nv_bfloat16 *hi,
+                                    __nv_bfloat16 *lo, int64_t ld) {
+  const int64_t total = rows * ld;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / ld;
+    const int cc = (int)(t - r * ld);
+    const float v = cc < cols ? in[r * cols + cc] : 0.f;
+    __nv_bfloat16 h, l;
+    split1(v, h, l);
+    hi[t] = h;
+    lo[t] = l;
+  }
+}
+
 __global__ void set_ones_col_kernel(__nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t rows, int64_t ld, int col) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     hi[r * ld + col] = __float2bfloat16_rn(1.0f);
@@ -253,6 +267,17 @@ __global__ void dot_finish_kernel(const float *__restrict__ partial, int64_t M, 
 }
 
 }  // namespace
+
+void launch_f32_to_split(Ctx &c, const float *in, int64_t rows, int cols, __nv_bfloat16 *hi, __nv_bfloat16 *lo,
+                         int64_t ld) {
+  if (rows <= 0) return;
+  int grid = (int)std::min<int64_t>((rows * ld + 255) / 256, (int64_t)c.num_sms * 8);
+  c.timer.begin(KC_TRAIN_EW, c.stream);
+  f32_to_split_kernel<<<grid, 256, 0, c.stream>>>(in, rows, cols, hi, lo, ld);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_TRAIN_EW);
+}
 
 void launch_set_ones_col(Ctx &c, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t rows, int64_t ld, int col) {
   if (rows <= 0) return;
