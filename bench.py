@@ -337,18 +337,26 @@ def run_b200(args, pkg):
         return
 
     pk = peaks()
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists() and N == w.N and K == w.K:
+        traffic = json.loads(tf.read_text()).get(args.config, {}).get("traffic_bytes_per_launch")
     tensor_bound = max(w.widths[1:-1] or [0]) >= 256
     if tensor_bound:
         ach = st["gemm_flops"] / (st["ms_gemm"] * 1e-3) / 1e12 if st["ms_gemm"] > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "dense-layer GEMM (fused bias+activation)", "achieved": ach,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": traffic,
+                "executed_tflops": 3 * ach,
                 "peak_source": f"{pk['src']} bf16 sustained", "launches": st["n_gemm_launches"],
                 "avg_launch_ms": st["ms_gemm"] / max(1, st["n_gemm_launches"]),
-                "note": "algorithmic 2*M*N*K flops of all GEMM launches / their CUDA-event time"}
+                "note": "algorithmic 2*M*N*K flops of all GEMM launches / their CUDA-event time; every k-slice is "
+                        "3 bf16 MMAs (hi*hi, hi*lo, lo*hi) to keep fp32 accuracy, so frac <= 1/3 by construction and "
+                        "executed_tflops = 3*achieved is what the tensor pipe runs; traffic = mean dram bytes per "
+                        "launch from profiles/traffic.json (ncu)"}
     else:
         ach = st["featurize_bytes"] / (st["ms_featurize"] * 1e-3) / 1e9 if st["ms_featurize"] > 0 else 0.0
         roof = {"bound": "hbm", "kernel": "featurize_ln_kernel (pair distances + LayerNorm)", "achieved": ach,
-                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic,
                 "peak_source": pk["src"], "launches": st["n_featurize_launches"],
                 "avg_launch_ms": st["ms_featurize"] / max(1, st["n_featurize_launches"]),
                 "note": "algorithmic 4*(D+F) bytes per record / CUDA-event time of the featurizer launches"}
