@@ -122,6 +122,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 256-bit global store (sm_100, PTX ISA 8.8): one full 32-byte sector per lane and half the LSU instructions
+__device__ __forceinline__ void st_global_v8(void *ptr, const uint32_t *v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 __device__ __forceinline__ float act_fwd(float a, int kind) {
   switch (kind) {
     case ISOKANN_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-a));
@@ -154,6 +161,7 @@ struct TcParams {
   int M, N, K;          // D is M x N, reduction length K (elements)
   int m_tiles, n_tiles, splits, kb_per_split, num_kb;
   int epi, act, mn_major, ones_col;
+  int st_v8;            // split outputs are 32-byte aligned with a 32-byte multiple pitch: 256-bit stores
   const float *bias;    // [N] or nullptr
   __nv_bfloat16 *out_hi, *out_lo;  // split outputs, row-major, leading dimension ldo
   int64_t ldo;
@@ -452,12 +460,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         uint32_t ph[16], pl[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
-        uint4 *dh = reinterpret_cast<uint4 *>(p.out_hi + row * p.ldo + col0);
-        uint4 *dl = reinterpret_cast<uint4 *>(p.out_lo + row * p.ldo + col0);
+        __nv_bfloat16 *dh = p.out_hi + row * p.ldo + col0;
+        __nv_bfloat16 *dl = p.out_lo + row * p.ldo + col0;
+        if (p.st_v8) {
+          st_global_v8(dh, ph);
+          st_global_v8(dh + 16, ph + 8);
+          st_global_v8(dl, pl);
+          st_global_v8(dl + 16, pl + 8);
+        } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          dh[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-          dl[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+          for (int q = 0; q < 4; ++q) {
+            reinterpret_cast<uint4 *>(dh)[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+            reinterpret_cast<uint4 *>(dl)[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+          }
         }
       }
       if (EPI == TC_EPI_TAIL && row_ok && half == 0) {
@@ -599,6 +614,7 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   p.f32_vec = (((uintptr_t)g.out_f32 & 15) == 0 && (g.ldc & 3) == 0 && (((int64_t)g.M * g.ldc) & 3) == 0) ? 1 : 0;
   p.z_hi = g.z_hi; p.z_lo = g.z_lo; p.ldz = g.ldz;
   p.tail = g.tail; p.chi_out = g.chi_out;
+  p.st_v8 = (((uintptr_t)g.out_hi & 31) == 0 && ((uintptr_t)g.out_lo & 31) == 0 && (g.ldo * 2) % 32 == 0) ? 1 : 0;
   p.w_last = g.w_last; p.dot_out = g.dot_out; p.d = g.d; p.dot_slots = 2 * p.n_tiles;
   if (g.epi == TC_EPI_BIAS_ACT_SPLIT || g.epi == TC_EPI_MULDACT_SPLIT)
     IK_REQUIRE(g.ldo % 8 == 0 && g.ldo >= (int64_t)p.n_tiles * 0 + ((g.N + 31) / 32) * 32, ISOKANN_BAD_ARGUMENT,
