@@ -166,6 +166,12 @@ int32_t isokann_featurize(isokann_ctx *ctx, const float *coords, int64_t D, int6
  * (coordinates, is_features == 0) or rows == F (features, is_features == 1) -> d x M */
 int32_t isokann_forward(isokann_ctx *ctx, const float *in, int64_t rows, int64_t M, int32_t is_features,
                         float *chi_out);
+/* Vector-Jacobian product of model(featurizer(x)) w.r.t. x: grad_out[rows x M] = d(sum(cot .* chi(x)))/dx.
+ * dchidx(iso, x) / dchidfeat(iso, feat) (src/utils/minimumpath.jl:3-13) with cot == NULL (ones); the pullback
+ * of the featurizer replaces sqpairdist_bwd_kernel! (src/utils/pairdists.jl:153-167,179-196), which the
+ * metadynamics bias (src/simulators/metadynamics.jl:40-49) and optimal control differentiate through. */
+int32_t isokann_chi_vjp(isokann_ctx *ctx, const float *in, int64_t rows, int64_t M, int32_t is_features,
+                        const float *cot, float *grad_out);
 /* chis(iso) on the resident xs -> d x N */
 int32_t isokann_chis(isokann_ctx *ctx, float *chi_out);
 /* expectation(model, propfeatures(data)) (src/isotarget.jl:18,20) on the resident ys -> d x N */

@@ -145,17 +145,19 @@ void forward_rows_tcn(Ctx &c, const float *in, const int64_t *gather, int64_t go
 
 // keep: the backward pass will need every layer's activations (training step)
 void forward_rows(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords,
-                  bool keep = false) {
+                  bool keep = false, bool force_fp32 = false) {
   if (M <= 0) return;
-  if (c.tc) {
+  if (force_fp32) {
+    // fall through to the FP32 CUDA-core path below (keeps fp32 activations for a backward pass)
+  } else if (c.tc) {
     forward_rows_tc(c, in, gather, goff, M, in_is_coords, keep);
     return;
   }
-  if (c.tcn && !keep) {
+  if (!force_fp32 && c.tcn && !keep) {
     forward_rows_tcn(c, in, gather, goff, M, in_is_coords);
     return;
   }
-  if (c.tiny && !keep && gather == nullptr) {
+  if (!force_fp32 && c.tiny && !keep && gather == nullptr) {
     c.act[c.L].ensure((size_t)M * c.d);
     launch_tiny_forward(c, in, M, c.act[c.L].p);
     return;
@@ -921,6 +923,24 @@ void build_pair_table(Ctx &c) {
   if (!tab.empty()) {
     c.pairs.ensure(tab.size());
     IK_CUDA(cudaMemcpy(c.pairs.p, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    // atom -> incident features, for the featurizer pullback
+    const int A = g.n_atoms;
+    std::vector<int> off(A + 1, 0);
+    for (const int2 &p : tab) {
+      off[p.x / 3 + 1]++;
+      off[p.y / 3 + 1]++;
+    }
+    for (int a = 0; a < A; ++a) off[a + 1] += off[a];
+    std::vector<int2> adj(2 * tab.size());
+    std::vector<int> fill(off.begin(), off.end() - 1);
+    for (int f = 0; f < (int)tab.size(); ++f) {
+      adj[fill[tab[f].x / 3]++] = make_int2(f, tab[f].y);
+      adj[fill[tab[f].y / 3]++] = make_int2(f, tab[f].x);
+    }
+    c.adj_off.ensure(off.size());
+    c.adj.ensure(adj.size());
+    IK_CUDA(cudaMemcpy(c.adj_off.p, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    IK_CUDA(cudaMemcpy(c.adj.p, adj.data(), adj.size() * sizeof(int2), cudaMemcpyHostToDevice));
   }
 }
 
@@ -1073,6 +1093,8 @@ int32_t isokann_destroy(isokann_ctx *c) {
     delete c->tcs;
   }
   c->pairs.release();
+  c->adj_off.release();
+  c->adj.release();
   c->red_d.release();
   c->epoch_loss.release();
   c->red_am.release();
@@ -1253,6 +1275,65 @@ int32_t isokann_forward(isokann_ctx *c, const float *in, int64_t rows, int64_t M
                               cudaMemcpyHostToDevice, c->stream));
       forward_rows(*c, c->staging_in.p, nullptr, 0, m, coords);
       IK_CUDA(cudaMemcpyAsync(chi_out + m0 * c->d, c->act[c->L].p, (size_t)m * c->d * sizeof(float),
+                              cudaMemcpyDeviceToHost, c->stream));
+      sync_stream(*c);
+    }
+    c->timer.flush(c->stream);
+  });
+}
+
+int32_t isokann_chi_vjp(isokann_ctx *c, const float *in, int64_t rows, int64_t M, int32_t is_features,
+                        const float *cot, float *grad_out) {
+  return guarded(c, [&] {
+    IK_REQUIRE(in && grad_out, ISOKANN_BAD_ARGUMENT, "NULL buffer");
+    const bool coords = !is_features;
+    IK_REQUIRE(rows == (coords ? c->D : c->F), ISOKANN_BAD_ARGUMENT, "row count does not match the model input");
+    const bool pairs = coords && c->cfg.featurizer != ISOKANN_FEAT_IDENTITY;
+    const int L = c->L, d = c->d, F = c->F;
+    const int64_t ch = std::min<int64_t>(chunk_rows(*c, 1), 16384);
+    const int64_t mc = std::min(ch, std::max<int64_t>(M, 1));
+    c->staging_in.ensure((size_t)mc * rows);
+    c->staging_out.ensure((size_t)mc * std::max<int64_t>(rows, F));
+    c->delta_a.ensure((size_t)mc * std::max(c->maxw, d));
+    c->delta_b.ensure((size_t)mc * std::max(c->maxw, d));
+    DevBuf<float> &cotbuf = c->red_f;
+    cotbuf.ensure((size_t)std::max<int64_t>(2048, mc * d));
+    for (int64_t m0 = 0; m0 < M; m0 += ch) {
+      const int64_t m = std::min(ch, M - m0);
+      IK_CUDA(cudaMemcpyAsync(c->staging_in.p, in + m0 * rows, (size_t)m * rows * sizeof(float),
+                              cudaMemcpyHostToDevice, c->stream));
+      if (cot)
+        IK_CUDA(cudaMemcpyAsync(cotbuf.p, cot + m0 * d, (size_t)m * d * sizeof(float), cudaMemcpyHostToDevice,
+                                c->stream));
+      forward_rows(*c, c->staging_in.p, nullptr, 0, m, coords, true, true);
+      float *cur = c->delta_a.p, *other = c->delta_b.p;
+      launch_vjp_seed(*c, c->act[L].p, cot ? cotbuf.p : nullptr, m, d, c->cfg.last_activation, cur);
+      for (int l = L - 1; l >= 1; --l) {  // delta_{l-1} = (delta_l * W_l^T) .* act'(z_{l-1})
+        const int fin = c->cfg.widths[l], fout = c->cfg.widths[l + 1];
+        GemmP g{};
+        g.A = cur; g.lda = fout;
+        g.B = c->params.p + c->off_w[l]; g.ldb = fout;
+        g.C = other; g.ldc = fin;
+        g.Z = c->act[l].p; g.ldz = fin;
+        g.M = (int)m; g.N = fin; g.K = fout;
+        g.ones_k = -1; g.ones_i = -1;
+        g.act = c->cfg.activation; g.epi = EPI_MULDACT;
+        launch_gemm(*c, g, true, false, 1);
+        std::swap(cur, other);
+      }
+      {  // dL/dx_hat = delta_1 * W1'^T (folded first layer), no activation in front of it
+        const int fout = c->cfg.widths[1];
+        GemmP g{};
+        g.A = cur; g.lda = fout;
+        g.B = layer_segment(*c, 0); g.ldb = fout;
+        g.C = other; g.ldc = F;
+        g.M = (int)m; g.N = F; g.K = fout;
+        g.ones_k = -1; g.ones_i = -1;
+        g.act = ISOKANN_ACT_IDENTITY; g.epi = EPI_ACT;
+        launch_gemm(*c, g, true, false, 1);
+      }
+      launch_featurize_backward(*c, c->staging_in.p, m, pairs, c->ln, other, c->staging_out.p);
+      IK_CUDA(cudaMemcpyAsync(grad_out + m0 * rows, c->staging_out.p, (size_t)m * rows * sizeof(float),
                               cudaMemcpyDeviceToHost, c->stream));
       sync_stream(*c);
     }

@@ -116,6 +116,9 @@ struct Ctx;
 void launch_featurize(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M, bool pairs,
                       bool do_ln, float *out, int64_t ldo);
 int launch_gemm(Ctx &c, const GemmP &p, bool a_kcontig, bool b_jcontig, int splits);  // returns splits used
+void launch_featurize_backward(Ctx &c, const float *in, int64_t M, bool pairs, bool do_ln, const float *gxhat,
+                               float *out);
+void launch_vjp_seed(Ctx &c, const float *chi, const float *cot, int64_t M, int d, int lastact, float *delta);
 void launch_splitk_reduce(Ctx &c, const float *partials, int splits, int64_t count, float *out);
 void launch_kmean(Ctx &c, const float *chi, const float *weights, int64_t n, int K, int d, float *out);
 void launch_minmax(Ctx &c, const float *x, int64_t n, float *partials, int *nblocks_out);
@@ -185,6 +188,9 @@ struct Ctx {
   TcState *tcs = nullptr;
   DevBuf<int2> pairs;  // coordinate offsets (3a, 3b) per feature
   int n_pairs = 0;
+  // atom -> incident features (CSR), for the featurizer pullback: adj[e] = (feature, coordinate offset of the other atom)
+  DevBuf<int> adj_off;
+  DevBuf<int2> adj;
 
   // resident data
   DevBuf<float> xs_own, ys_own, kweights;

@@ -229,6 +229,118 @@ static void launch_reg(Ctx &c, const float *coords, const int64_t *gather, int64
       out_lo);
 }
 
+// Pullback of featurizer + LayerNorm (reference: sqpairdist_bwd_kernel! and its rrule,
+// src/utils/pairdists.jl:153-167,179-196, used by dchidx src/utils/minimumpath.jl:3-7 and the metadynamics
+// bias src/simulators/metadynamics.jl:40-49).  One warp per record: recompute the distances and the
+// LayerNorm statistics, turn dL/dx_hat into dL/df (LayerNorm backward), then every lane owns atoms and
+// walks their incident features (CSR built once per context) -- no atomics, deterministic.
+__global__ void __launch_bounds__(256) featurize_backward_kernel(const float *__restrict__ in, int64_t M, int D, int F,
+                                                                 const int2 *__restrict__ pairs,
+                                                                 const int *__restrict__ adj_off,
+                                                                 const int2 *__restrict__ adj, int do_ln, float eps2,
+                                                                 const float *__restrict__ gxhat,
+                                                                 float *__restrict__ out, int Dp, int Fp) {
+  extern __shared__ float sm[];
+  const int warps = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *sc = sm + (size_t)w * (Dp + 2 * Fp);
+  float *sf = sc + Dp;   // features, then x_hat
+  float *sg = sf + Fp;   // dL/dx_hat, then dL/df (/ f for distance features)
+  for (int64_t m = (int64_t)blockIdx.x * warps + w; m < M; m += (int64_t)gridDim.x * warps) {
+    const float *c = in + m * D;
+    for (int i = lane; i < D; i += 32) sc[i] = __ldg(c + i);
+    __syncwarp();
+    float s = 0.f;
+    for (int f = lane; f < F; f += 32) {
+      float v;
+      if (pairs) {
+        const int2 p = __ldg(pairs + f);
+        const float dx = sc[p.x] - sc[p.y], dy = sc[p.x + 1] - sc[p.y + 1], dz = sc[p.x + 2] - sc[p.y + 2];
+        v = sqrtf(fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 0.f));
+      } else {
+        v = sc[f];
+      }
+      sf[f] = v;
+      sg[f] = __ldg(gxhat + m * F + f);
+      s += v;
+    }
+    if (do_ln) {
+      const float mu = warp_sum(s) / (float)F;
+      float q = 0.f;
+      for (int f = lane; f < F; f += 32) {
+        const float t = sf[f] - mu;
+        q = fmaf(t, t, q);
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)F + eps2);
+      float s1 = 0.f, s2 = 0.f;
+      for (int f = lane; f < F; f += 32) {
+        const float xh = (sf[f] - mu) * rstd;
+        s1 += sg[f];
+        s2 = fmaf(sg[f], xh, s2);
+      }
+      s1 = warp_sum(s1) / (float)F;
+      s2 = warp_sum(s2) / (float)F;
+      for (int f = lane; f < F; f += 32) {
+        const float xh = (sf[f] - mu) * rstd;
+        sg[f] = rstd * (sg[f] - s1 - xh * s2);   // dL/df
+      }
+    }
+    if (!pairs) {
+      for (int f = lane; f < F; f += 32) out[m * D + f] = sg[f];
+    } else {
+      for (int f = lane; f < F; f += 32) sg[f] = sf[f] > 0.f ? sg[f] / sf[f] : 0.f;
+      __syncwarp();
+      const int A = D / 3;
+      for (int a = lane; a < A; a += 32) {
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        const float ax = sc[3 * a], ay = sc[3 * a + 1], az = sc[3 * a + 2];
+        for (int e = adj_off[a]; e < adj_off[a + 1]; ++e) {
+          const int2 q = __ldg(adj + e);
+          const float wv = sg[q.x];
+          gx = fmaf(wv, ax - sc[q.y], gx);
+          gy = fmaf(wv, ay - sc[q.y + 1], gy);
+          gz = fmaf(wv, az - sc[q.y + 2], gz);
+        }
+        out[m * D + 3 * a] = gx;
+        out[m * D + 3 * a + 1] = gy;
+        out[m * D + 3 * a + 2] = gz;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+void launch_featurize_backward(Ctx &c, const float *in, int64_t M, bool pairs, bool do_ln, const float *gxhat,
+                               float *out) {
+  if (M <= 0) return;
+  const int D = pairs ? c.D : c.F;
+  const int F = c.F;
+  const int Dp = (D + 3) & ~3, Fp = (F + 3) & ~3;
+  int warps = 8;
+  size_t smem = (size_t)warps * (Dp + 2 * Fp) * sizeof(float);
+  while (smem > 200 * 1024 && warps > 1) {
+    warps >>= 1;
+    smem = (size_t)warps * (Dp + 2 * Fp) * sizeof(float);
+  }
+  IK_REQUIRE(smem <= 200 * 1024, ISOKANN_BAD_ARGUMENT, "feature dimension too large for the featurizer pullback");
+  static bool attr_set = false;
+  if (!attr_set) {
+    IK_CUDA(cudaFuncSetAttribute(featurize_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  int64_t want = (M + warps - 1) / warps;
+  int grid = (int)std::min<int64_t>(want, (int64_t)c.num_sms * 8);
+  const float eps = c.cfg.ln_eps;
+  c.timer.begin(KC_FEATURIZE, c.stream);
+  featurize_backward_kernel<<<grid, warps * 32, smem, c.stream>>>(in, M, D, F, pairs ? c.pairs.p : nullptr,
+                                                                  pairs ? c.adj_off.p : nullptr,
+                                                                  pairs ? c.adj.p : nullptr, do_ln ? 1 : 0, eps * eps,
+                                                                  gxhat, out, Dp, Fp);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_FEATURIZE);
+}
+
 static void launch_featurize_impl(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M,
                                   bool pairs, bool do_ln, float *out, int64_t ldo, __nv_bfloat16 *out_hi,
                                   __nv_bfloat16 *out_lo) {

@@ -93,6 +93,22 @@ void launch_loss_delta(Ctx &c, const float *chi, const float *target, const int6
   c.count_launch(KC_TRAIN_EW);
 }
 
+// seed of a vector-Jacobian product: delta = cot .* act'(chi)   (cot == nullptr: ones)
+__global__ void vjp_seed_kernel(const float *__restrict__ chi, const float *__restrict__ cot, int64_t total,
+                                int lastact, float *__restrict__ delta) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+    delta[t] = (cot ? cot[t] : 1.0f) * dact_out(chi[t], lastact);
+}
+
+void launch_vjp_seed(Ctx &c, const float *chi, const float *cot, int64_t M, int d, int lastact, float *delta) {
+  const int64_t total = M * d;
+  if (total <= 0) return;
+  int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c.num_sms * 8);
+  vjp_seed_kernel<<<grid, 256, 0, c.stream>>>(chi, cot, total, lastact, delta);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_TRAIN_EW);
+}
+
 // LayerNorm affine folded into the first Dense layer: z0 = gamma .* xhat .+ beta, so
 //   W1 z0 + b1 = (W1 diag(gamma)) xhat + (b1 + W1 beta).
 // folded is the row-major (F+1) x h1 segment [W1' ; b1'] consumed by the GEMM.

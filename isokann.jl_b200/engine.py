@@ -204,6 +204,16 @@ class Engine:
         self._check(self.lib.isokann_forward(self.h, L.ptr(x), x.shape[0], M, int(is_features), L.ptr(out)))
         return out
 
+    def chi_vjp(self, x, cot=None, is_features: bool = False) -> np.ndarray:
+        """d(sum(cot .* model(x)))/dx for Julia-shaped x (rows, ...) -> same shape; cot (d, ...) defaults to ones"""
+        x = julia_f32(x)
+        lead = x.shape[1:]
+        M = int(np.prod(lead)) if lead else 1
+        ct = None if cot is None else julia_f32(cot)
+        out = np.empty(x.shape, dtype=np.float32, order="F")
+        self._check(self.lib.isokann_chi_vjp(self.h, L.ptr(x), x.shape[0], M, int(is_features), L.ptr(ct), L.ptr(out)))
+        return out
+
     def chis(self) -> np.ndarray:
         out = np.empty((self.d, self.N), dtype=np.float32, order="F")
         self._check(self.lib.isokann_chis(self.h, L.ptr(out)))

@@ -117,6 +117,21 @@ def chicoords(iso: Iso, xs) -> np.ndarray:
     return iso.engine.forward(xs, is_features=False)
 
 
+def dchidx(iso: Iso, x, cot=None) -> np.ndarray:
+    """dchidx(iso, x) (src/utils/minimumpath.jl:3-7): gradient of chi(x) w.r.t. the raw coordinates x (D,) or (D, M);
+    for multi-dimensional chi pass the cotangent ``cot`` (d, M) (vector-Jacobian product)"""
+    x = np.asarray(x)
+    g = iso.engine.chi_vjp(x.reshape(x.shape[0], -1), cot, is_features=False)
+    return g.reshape(x.shape)
+
+
+def dchidfeat(iso: Iso, feat, cot=None) -> np.ndarray:
+    """dchidfeat(iso, feat) (src/utils/minimumpath.jl:9-13): gradient w.r.t. the features"""
+    feat = np.asarray(feat)
+    g = iso.engine.chi_vjp(feat.reshape(feat.shape[0], -1), cot, is_features=True)
+    return g.reshape(feat.shape)
+
+
 def koopman(iso: Iso) -> np.ndarray:
     """koopman(iso) = expectation(model, propfeatures(data)) (src/isotarget.jl:20)"""
     return iso.engine.koopman()
@@ -155,6 +170,6 @@ def load_state(path: str, iso: Iso) -> Iso:
     return iso
 
 
-__all__ = ["Iso", "run_", "train_batch_", "isotarget", "chis", "chicoords", "koopman", "chi_kchi", "cpu", "save",
+__all__ = ["Iso", "dchidx", "dchidfeat", "run_", "train_batch_", "isotarget", "chis", "chicoords", "koopman", "chi_kchi", "cpu", "save",
            "load_state", "defaultmodel", "draw_perm", "DomainError", "TransformShiftscale", "TransformISA",
            "TransformPseudoInv"]

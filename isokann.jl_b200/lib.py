@@ -91,6 +91,7 @@ SIGNATURES = {
     "isokann_download_opt_state": (C.c_int32, [_p, _p, _p, _p, C.c_int64]),
     "isokann_featurize": (C.c_int32, [_p, _p, C.c_int64, C.c_int64, _p]),
     "isokann_forward": (C.c_int32, [_p, _p, C.c_int64, C.c_int64, C.c_int32, _p]),
+    "isokann_chi_vjp": (C.c_int32, [_p, _p, C.c_int64, C.c_int64, C.c_int32, _p, _p]),
     "isokann_chis": (C.c_int32, [_p, _p]),
     "isokann_koopman": (C.c_int32, [_p, _p]),
     "isokann_target": (C.c_int32, [_p, C.c_int32, C.POINTER(TargetOpts), _p]),

@@ -30,7 +30,7 @@ __all__ = [
     "indexmap", "myisa", "fixperm", "isotarget_shiftscale", "isotarget_isa",
     "isotarget_pinv", "isotarget", "OptConfig", "OptState", "opt_init",
     "opt_update", "loss_weights", "batch_loss_and_grad", "train_batch",
-    "run", "weighted_expectation",
+    "run", "weighted_expectation", "chi_vjp",
 ]
 
 F32 = np.float32
@@ -574,3 +574,49 @@ def run(m: Model, xsf: np.ndarray, ysf: np.ndarray, cfg: OptConfig, st: OptState
             losses.append(train_batch(m, xsf, t, cfg, st, minibatch, perms1[p]))
             p += 1
     return losses
+
+
+# ----------------------------------------------------------------------------------------------
+# gradient of chi w.r.t. coordinates  (dchidx / dchidfeat, src/utils/minimumpath.jl:3-13; the pullback of
+# the featurizer is src/utils/pairdists.jl:153-167,179-196) -- SURVEY section 8f, "next" row 1
+# ----------------------------------------------------------------------------------------------
+
+def chi_vjp(m: Model, x: np.ndarray, cot: Optional[np.ndarray] = None, pairs0: Optional[np.ndarray] = None):
+    """Vector-Jacobian product d(sum(cot .* chi(x)))/dx in float64.
+    x: (M, D) coordinate records (pairs0 = (F, 2) 0-based atom pairs) or (M, F) features (pairs0 None);
+    cot: (M, d) cotangent (default ones, i.e. Zygote.gradient of `chicoords(iso, x) |> only` for d = 1)."""
+    x = np.asarray(x, dtype=F64)
+    M = x.shape[0]
+    if pairs0 is not None:
+        c = x.reshape(M, -1, 3)
+        diff = c[:, pairs0[:, 0], :] - c[:, pairs0[:, 1], :]          # (M, F, 3)
+        f = np.sqrt(np.maximum((diff * diff).sum(-1), 0.0))
+    else:
+        f = x
+    z = f
+    if m.layernorm:
+        mu = f.mean(-1, keepdims=True)
+        xc = f - mu
+        r = 1.0 / np.sqrt((xc * xc).mean(-1, keepdims=True) + float(m.ln_eps) ** 2)
+        xh = xc * r
+        z = xh * m.ln_scale.astype(F64) + m.ln_bias.astype(F64)
+    zs = [z]
+    for i in range(m.nlayers):
+        a = z @ m.W[i].astype(F64) + m.b[i].astype(F64)
+        z = _act(a, m.act if i < m.nlayers - 1 else m.lastact)
+        zs.append(z)
+    g = np.ones_like(z) if cot is None else np.asarray(cot, dtype=F64)
+    for i in range(m.nlayers - 1, -1, -1):
+        g = g * _dact_from_out(zs[i + 1], m.act if i < m.nlayers - 1 else m.lastact)
+        g = g @ m.W[i].astype(F64).T
+    if m.layernorm:
+        g = g * m.ln_scale.astype(F64)
+        g = r * (g - g.mean(-1, keepdims=True) - xh * (g * xh).mean(-1, keepdims=True))
+    if pairs0 is None:
+        return g
+    w = np.where(f > 0, g / np.where(f > 0, f, 1.0), 0.0)                 # dL/df / f
+    contrib = w[:, :, None] * diff                                       # (M, F, 3): gradient w.r.t. atom a
+    out = np.zeros_like(c)
+    np.add.at(out, (np.arange(M)[:, None], pairs0[None, :, 0]), contrib)
+    np.add.at(out, (np.arange(M)[:, None], pairs0[None, :, 1]), -contrib)
+    return out.reshape(M, -1)

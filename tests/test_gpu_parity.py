@@ -341,3 +341,58 @@ def test_tiny_net_forward_kernel(pkg, oracle):
     assert np.allclose(r["chi0_lib"], r["chi0_ref"], rtol=TOL_CHI, atol=1e-5)
     assert np.allclose(r["loss_lib"], r["loss_ref"], rtol=1e-3)
     assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=1e-3, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------
+# gradient of chi w.r.t. coordinates / features ("next" row 1)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,widths", [("c1", [231, 38, 6, 1]), ("c3", [595, 71, 8, 1]), ("c4", [231, 38, 6, 3]),
+                                         ("c1", [231, 256, 256, 1])])
+def test_dchidx_matches_oracle(pkg, oracle, name, widths):
+    w = copy.deepcopy(pkg.synthetic.WORKLOADS[name])
+    w.widths = widths
+    M = 37
+    xs, ys = pkg.synthetic.make_data(w, M, 1)
+    om = oracle_model(oracle, w.widths, True, 5)
+    rng = np.random.default_rng(3)
+    om.ln_scale = rng.uniform(0.5, 1.5, w.F).astype(np.float32)
+    om.ln_bias = (0.1 * rng.normal(size=w.F)).astype(np.float32)
+    iso = make_iso(pkg, w, xs, ys, oracle.flatten_params(om), target="isa" if widths[-1] > 1 else "shiftscale")
+    pairs0 = oracle.pair_table(w.n_atoms)
+    d = widths[-1]
+    cot = None if d == 1 else np.asfortranarray(rng.normal(size=(d, M)).astype(np.float32))
+    g = pkg.dchidx(iso, xs, cot)                                        # (D, M)
+    ref = oracle.chi_vjp(om, records(xs), None if cot is None else records(cot), pairs0)
+    assert g.shape == xs.shape
+    assert np.abs(records(g) - ref).max() < 2e-3 * np.abs(ref).max()
+    # single configuration as a vector, like dchidx(iso, x) in the reference
+    g1 = pkg.dchidx(iso, xs[:, 0], None if cot is None else cot[:, :1])
+    assert np.allclose(g1, g[:, 0], rtol=1e-5, atol=1e-7)
+    # gradient w.r.t. the features (dchidfeat)
+    feats = iso.data.features()
+    gf = pkg.dchidfeat(iso, feats, cot)
+    reff = oracle.chi_vjp(om, records(feats), None if cot is None else records(cot), None)
+    assert np.abs(records(gf) - reff).max() < 2e-3 * np.abs(reff).max()
+
+
+def test_dchidx_identity_featurizer_and_subset_pairs(pkg, oracle):
+    # smallnet on raw coordinates (Langevin toy systems): gradient w.r.t. the coordinates themselves
+    w = pkg.synthetic.WORKLOADS["c2"]
+    xs, ys = pkg.synthetic.make_data(w, 50, 1)
+    om = oracle_model(oracle, w.widths, False, 5)
+    iso = make_iso(pkg, w, xs, ys, oracle.flatten_params(om))
+    g = pkg.dchidx(iso, xs)
+    ref = oracle.chi_vjp(om, records(xs), None, None)
+    assert np.abs(records(g) - ref).max() < 1e-4 * np.abs(ref).max()
+    # explicit pair list: atoms that appear in no pair get a zero gradient
+    w1 = pkg.synthetic.WORKLOADS["c1"]
+    xs1, ys1 = pkg.synthetic.make_data(w1, 20, 1)
+    pairs = [(1, 22), (5, 7), (9, 15), (2, 9), (7, 15), (5, 17)]
+    om1 = oracle_model(oracle, [6, 4, 1], True, 6)
+    data = pkg.SimulationData(xs1, ys1, featurizer=pkg.FeaturesPairs(pairs))
+    iso1 = pkg.Iso(data, model=pkg.Chain([6, 4, 1], True).load_flat(oracle.flatten_params(om1)))
+    g1 = records(pkg.dchidx(iso1, xs1))
+    ref1 = oracle.chi_vjp(om1, records(xs1), None, np.array(pairs) - 1)
+    assert np.abs(g1 - ref1).max() < 2e-3 * np.abs(ref1).max()
+    untouched = [a for a in range(22) if all(a + 1 not in p for p in pairs)]
+    assert np.abs(g1.reshape(20, 22, 3)[:, untouched, :]).max() == 0.0

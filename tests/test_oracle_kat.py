@@ -183,3 +183,33 @@ def test_gradient_matches_finite_differences(oracle):
         fm[k] -= h
         fd = (loss64(fp) - loss64(fm)) / (2 * h)
         assert abs(fd - g[k]) < 2e-3 * max(1.0, abs(fd)), (k, fd, g[k])
+
+
+def test_chi_vjp_matches_finite_differences(oracle):
+    rng = np.random.default_rng(8)
+    m = oracle.pairnet(15, nout=2, rng=rng)                 # 6 atoms -> 15 pair distances
+    m.ln_scale = rng.uniform(0.5, 1.5, 15).astype(np.float32)
+    m.ln_bias = (0.1 * rng.normal(size=15)).astype(np.float32)
+    pairs0 = oracle.pair_table(6)
+    x = rng.normal(size=(3, 18))
+    cot = rng.normal(size=(3, 2))
+
+    def scalar(xx):
+        f = oracle.flatpairdists(xx, out_dtype=np.float64)
+        mm = m
+        z = oracle.layernorm(f) * mm.ln_scale.astype(np.float64) + mm.ln_bias.astype(np.float64)
+        for i in range(mm.nlayers):
+            a = z @ mm.W[i].astype(np.float64) + mm.b[i].astype(np.float64)
+            z = oracle.sigmoid(a) if i < mm.nlayers - 1 else a
+        return float((z * cot).sum())
+    g = oracle.chi_vjp(m, x, cot, pairs0)
+    for _ in range(20):
+        i, k = rng.integers(0, 3), rng.integers(0, 18)
+        h = 1e-6
+        xp, xm = x.copy(), x.copy()
+        xp[i, k] += h
+        xm[i, k] -= h
+        fd = (scalar(xp) - scalar(xm)) / (2 * h)
+        assert abs(fd - g[i, k]) < 1e-6 * max(1.0, abs(fd)), (fd, g[i, k])
+    # rigid translation does not change chi: the gradient sums to zero over atoms
+    assert np.abs(g.reshape(3, 6, 3).sum(axis=1)).max() < 1e-12
