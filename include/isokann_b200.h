@@ -145,6 +145,16 @@ int32_t isokann_set_data_sharded(isokann_ctx *ctx, const float *xs, const float 
  * isokann_synchronize) has returned. */
 int32_t isokann_set_data_async(isokann_ctx *ctx, const float *xs, const float *ys_local, int64_t D, int64_t K,
                                int64_t N, int64_t n_offset, int64_t n_local);
+/* addcoords!(iso, coords) / mergedata (src/simulation.jl:162-185, src/iso.jl:238): append n_new start points and
+ * their K Koopman samples to the resident data without re-uploading what is already there (single rank;
+ * data must be library-owned).  The resident target becomes invalid, as in the reference where run! recomputes it. */
+int32_t isokann_append_data(isokann_ctx *ctx, const float *xs_new, const float *ys_new, int64_t D, int64_t K,
+                            int64_t n_new);
+/* iso.data = iso.data[end-cutoff+1:end] of run_kde! (src/iso.jl:288-290): keep the newest n_keep start points */
+int32_t isokann_keep_last(isokann_ctx *ctx, int64_t n_keep);
+/* model(flattenlast(propfeatures(data))) of resample_kde / chistratcoords (src/simulation.jl:199-207,227-228):
+ * chi of every resident Koopman sample, d x K x N, no K-mean */
+int32_t isokann_chis_prop(isokann_ctx *ctx, float *chi_out);
 /* Same with buffers already resident on this context's device (no copy of ys: it is adopted by
  * reference and must stay alive until the next set_data / destroy). */
 int32_t isokann_set_data_dev(isokann_ctx *ctx, const float *dev_xs, const float *dev_ys_local, int64_t D, int64_t K,

@@ -1174,6 +1174,97 @@ int32_t isokann_set_data_async(isokann_ctx *c, const float *xs, const float *ys_
   return guarded(c, [&] { set_data_impl(*c, xs, ys_local, false, false, D, K, N, n_offset, n_local, true); });
 }
 
+int32_t isokann_append_data(isokann_ctx *c, const float *xs_new, const float *ys_new, int64_t D, int64_t K,
+                            int64_t n_new) {
+  return guarded(c, [&] {
+    IK_REQUIRE(c->world == 1, ISOKANN_ERR_STATE, "isokann_append_data is single-rank only");
+    IK_REQUIRE(c->xs != nullptr && c->xs == c->xs_own.p && (c->K == 0 || c->ys == c->ys_own.p), ISOKANN_ERR_STATE,
+               "append needs library-owned data (isokann_set_data)");
+    IK_REQUIRE(xs_new && D == c->D && n_new >= 0 && (c->K == 0 || (ys_new && K == c->K)), ISOKANN_BAD_ARGUMENT,
+               "appended block must match D and K of the resident data");
+    if (c->ys_chunk_pts > 0) {
+      IK_CUDA(cudaStreamSynchronize(c->copy_stream));
+      c->ys_chunk_pts = 0;
+    }
+    if (n_new == 0) return;
+    const int64_t N0 = c->N, N1 = N0 + n_new;
+    auto grow = [&](DevBuf<float> &buf, int64_t per_point) {
+      if ((size_t)(N1 * per_point) <= buf.n) return;
+      DevBuf<float> nb;
+      nb.ensure((size_t)(std::max<int64_t>(N1, N0 + N0 / 2) * per_point));  // amortised growth
+      IK_CUDA(cudaMemcpyAsync(nb.p, buf.p, (size_t)N0 * per_point * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+      sync_stream(*c);
+      buf.release();
+      buf = nb;
+    };
+    grow(c->xs_own, D);
+    IK_CUDA(cudaMemcpyAsync(c->xs_own.p + N0 * D, xs_new, (size_t)n_new * D * sizeof(float), cudaMemcpyHostToDevice,
+                            c->stream));
+    c->xs = c->xs_own.p;
+    if (c->K > 0) {
+      grow(c->ys_own, c->K * D);
+      IK_CUDA(cudaMemcpyAsync(c->ys_own.p + N0 * c->K * D, ys_new, (size_t)n_new * c->K * D * sizeof(float),
+                              cudaMemcpyHostToDevice, c->stream));
+      c->ys = c->ys_own.p;
+    }
+    sync_stream(*c);
+    c->N = N1;
+    c->n_loc = N1;
+    c->has_target = false;
+    c->has_weights = false;
+  });
+}
+
+int32_t isokann_keep_last(isokann_ctx *c, int64_t n_keep) {
+  return guarded(c, [&] {
+    IK_REQUIRE(c->world == 1, ISOKANN_ERR_STATE, "isokann_keep_last is single-rank only");
+    IK_REQUIRE(c->xs != nullptr && c->xs == c->xs_own.p && (c->K == 0 || c->ys == c->ys_own.p), ISOKANN_ERR_STATE,
+               "keep_last needs library-owned data (isokann_set_data)");
+    IK_REQUIRE(n_keep >= 1, ISOKANN_BAD_ARGUMENT, "n_keep must be positive");
+    if (n_keep >= c->N) return;
+    const int64_t drop = c->N - n_keep;
+    auto shift = [&](DevBuf<float> &buf, int64_t per_point) {
+      DevBuf<float> nb;
+      nb.ensure(buf.n);
+      IK_CUDA(cudaMemcpyAsync(nb.p, buf.p + drop * per_point, (size_t)n_keep * per_point * sizeof(float),
+                              cudaMemcpyDeviceToDevice, c->stream));
+      sync_stream(*c);
+      buf.release();
+      buf = nb;
+    };
+    shift(c->xs_own, c->D);
+    c->xs = c->xs_own.p;
+    if (c->K > 0) {
+      shift(c->ys_own, c->K * c->D);
+      c->ys = c->ys_own.p;
+    }
+    c->N = n_keep;
+    c->n_loc = n_keep;
+    c->has_target = false;
+    c->has_weights = false;
+  });
+}
+
+int32_t isokann_chis_prop(isokann_ctx *c, float *chi_out) {
+  return guarded(c, [&] {
+    IK_REQUIRE(c->ys != nullptr && chi_out, ISOKANN_ERR_STATE, "no Koopman samples resident / NULL output");
+    const int64_t ch = chunk_rows(*c, 1);
+    const int64_t M = c->n_loc * c->K;
+    for (int64_t m0 = 0; m0 < M; m0 += ch) {
+      const int64_t m = std::min(ch, M - m0);
+      if (c->ys_chunk_pts > 0) {
+        const int64_t last = std::min<int64_t>((m0 + m - 1) / c->K / c->ys_chunk_pts, c->ys_chunks_pending - 1);
+        IK_CUDA(cudaStreamWaitEvent(c->stream, c->ys_events[(size_t)last], 0));
+      }
+      forward_rows(*c, c->ys + m0 * c->D, nullptr, 0, m, true);
+      IK_CUDA(cudaMemcpyAsync(chi_out + m0 * c->d, c->act[c->L].p, (size_t)m * c->d * sizeof(float),
+                              cudaMemcpyDeviceToHost, c->stream));
+      sync_stream(*c);
+    }
+    c->timer.flush(c->stream);
+  });
+}
+
 int32_t isokann_set_data_dev(isokann_ctx *c, const float *dev_xs, const float *dev_ys_local, int64_t D, int64_t K,
                              int64_t N, int64_t n_offset, int64_t n_local) {
   return guarded(c, [&] { set_data_impl(*c, dev_xs, dev_ys_local, false, true, D, K, N, n_offset, n_local); });

@@ -150,6 +150,23 @@ class Engine:
         self._check(self.lib.isokann_set_data_async(self.h, L.ptr(xs), L.ptr(ys), D, K, N, n_offset, n_local))
         self.N, self.K = N, K
 
+    def append_data(self, xs_new, ys_new):
+        xs_new = julia_f32(xs_new, 2)
+        ys_new = None if ys_new is None else julia_f32(ys_new, 3)
+        D, n = xs_new.shape
+        K = 0 if ys_new is None else ys_new.shape[1]
+        self._check(self.lib.isokann_append_data(self.h, L.ptr(xs_new), L.ptr(ys_new), D, K, n))
+        self.N += n
+
+    def keep_last(self, n_keep: int):
+        self._check(self.lib.isokann_keep_last(self.h, int(n_keep)))
+        self.N = min(self.N, int(n_keep))
+
+    def chis_prop(self) -> np.ndarray:
+        out = np.empty((self.d, self.K, self.N), dtype=np.float32, order="F")
+        self._check(self.lib.isokann_chis_prop(self.h, L.ptr(out)))
+        return out
+
     def set_data_dev(self, dev_xs, dev_ys, D: int, K: int, N: int, n_offset: int = 0, n_local: Optional[int] = None):
         """device-resident float32 buffers (torch tensors or raw addresses), records layout."""
         n_local = N if n_local is None else n_local

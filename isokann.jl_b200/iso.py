@@ -132,6 +132,30 @@ def dchidfeat(iso: Iso, feat, cot=None) -> np.ndarray:
     return g.reshape(feat.shape)
 
 
+def addcoords_(iso: Iso, xs_new, ys_new):
+    """addcoords!(iso, coords) (src/iso.jl:238, src/simulation.jl:183-185).  The reference propagates ``coords`` with
+    its simulation to obtain ys; simulators stay on the host here, so the caller passes the propagated samples.
+    Only the new block is uploaded."""
+    xs_new, ys_new = np.asarray(xs_new), np.asarray(ys_new)
+    iso.engine.append_data(xs_new, ys_new)
+    xs, ys = iso.data.coords
+    iso.data = SimulationData(iso.data.sim, (np.concatenate([xs, xs_new], axis=1), np.concatenate([ys, ys_new], axis=2)),
+                              featurizer=iso.data.featurizer)
+
+
+def cutoff_(iso: Iso, cutoff: int):
+    """iso.data = iso.data[end-cutoff+1:end] (run_kde!, src/iso.jl:288-290)"""
+    if len(iso.data) > cutoff:
+        iso.engine.keep_last(cutoff)
+        iso.data = iso.data[slice(len(iso.data) - cutoff, None)]
+
+
+def propchis(iso: Iso) -> np.ndarray:
+    """chi of every Koopman sample, (d, K, N): model(propfeatures(data)) as used by resample_kde / chistratcoords
+    (src/simulation.jl:199-207,227-228)"""
+    return iso.engine.chis_prop()
+
+
 def koopman(iso: Iso) -> np.ndarray:
     """koopman(iso) = expectation(model, propfeatures(data)) (src/isotarget.jl:20)"""
     return iso.engine.koopman()
@@ -170,6 +194,6 @@ def load_state(path: str, iso: Iso) -> Iso:
     return iso
 
 
-__all__ = ["Iso", "dchidx", "dchidfeat", "run_", "train_batch_", "isotarget", "chis", "chicoords", "koopman", "chi_kchi", "cpu", "save",
+__all__ = ["Iso", "dchidx", "dchidfeat", "addcoords_", "cutoff_", "propchis", "run_", "train_batch_", "isotarget", "chis", "chicoords", "koopman", "chi_kchi", "cpu", "save",
            "load_state", "defaultmodel", "draw_perm", "DomainError", "TransformShiftscale", "TransformISA",
            "TransformPseudoInv"]

@@ -83,6 +83,9 @@ SIGNATURES = {
     "isokann_set_data_f64": (C.c_int32, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64]),
     "isokann_set_data_sharded": (C.c_int32, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "isokann_set_data_async": (C.c_int32, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "isokann_append_data": (C.c_int32, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64]),
+    "isokann_keep_last": (C.c_int32, [_p, C.c_int64]),
+    "isokann_chis_prop": (C.c_int32, [_p, _p]),
     "isokann_set_data_dev": (C.c_int32, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "isokann_set_koopman_weights": (C.c_int32, [_p, _p]),
     "isokann_upload_params": (C.c_int32, [_p, _p, C.c_int64]),

@@ -396,3 +396,38 @@ def test_dchidx_identity_featurizer_and_subset_pairs(pkg, oracle):
     assert np.abs(g1 - ref1).max() < 2e-3 * np.abs(ref1).max()
     untouched = [a for a in range(22) if all(a + 1 not in p for p in pairs)]
     assert np.abs(g1.reshape(20, 22, 3)[:, untouched, :]).max() == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# incremental data ("next" row 2): addcoords!, cutoff window, chi of all Koopman samples
+# ---------------------------------------------------------------------------------------------
+def test_append_cutoff_and_propchis(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    N, K = 300, 3
+    xs, ys = pkg.synthetic.make_data(w, N, K)
+    flat = oracle.flatten_params(oracle_model(oracle, w.widths, True, 5))
+    full = make_iso(pkg, w, xs, ys, flat, minibatch=50)
+    grown = make_iso(pkg, w, xs[:, :120], ys[:, :, :120], flat, minibatch=50)
+    pkg.addcoords_(grown, xs[:, 120:200], ys[:, :, 120:200])          # two appends, second forces a reallocation
+    pkg.addcoords_(grown, xs[:, 200:], ys[:, :, 200:])
+    assert len(grown.data) == N and grown.engine.N == N
+    assert np.array_equal(pkg.koopman(grown), pkg.koopman(full))
+    assert np.array_equal(pkg.chis(grown), pkg.chis(full))
+    # chi of every Koopman sample: (d, K, N); its K-mean is the Koopman expectation
+    pc = pkg.propchis(full)
+    assert pc.shape == (1, K, N)
+    om = oracle.unflatten_params(oracle.Model(list(w.widths), True), flat)
+    _, ysf = oracle_features(oracle, w, xs, ys)
+    assert np.allclose(records(pc), oracle.forward(om, ysf), rtol=TOL_CHI, atol=5e-5)
+    # training on the grown data set equals training on the full one
+    perms = pkg.synthetic.make_perms(w, N, 2)
+    pkg.run_(grown, 2, perms=perms)
+    pkg.run_(full, 2, perms=perms)
+    assert grown.losses == full.losses
+    # cutoff window keeps the newest points
+    pkg.cutoff_(grown, 100)
+    tail = make_iso(pkg, w, xs[:, 200:], ys[:, :, 200:], grown.engine.download_params(), minibatch=50)
+    assert len(grown.data) == 100
+    assert np.array_equal(pkg.koopman(grown), pkg.koopman(tail))
+    with pytest.raises(pkg.IsokannError):                               # the old target no longer matches the data
+        pkg.train_batch_(grown, np.arange(1, 101))
