@@ -147,14 +147,12 @@ void forward_rows_tcn(Ctx &c, const float *in, const int64_t *gather, int64_t go
 void forward_rows(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords,
                   bool keep = false, bool force_fp32 = false) {
   if (M <= 0) return;
-  if (force_fp32) {
-    // fall through to the FP32 CUDA-core path below (keeps fp32 activations for a backward pass)
-  } else if (c.tc) {
-    forward_rows_tc(c, in, gather, goff, M, in_is_coords, keep);
+  if (!force_fp32 && c.tcn && !keep) {  // narrow net inference: one GEMM with the MLP tail in its epilogue
+    forward_rows_tcn(c, in, gather, goff, M, in_is_coords);
     return;
   }
-  if (!force_fp32 && c.tcn && !keep) {
-    forward_rows_tcn(c, in, gather, goff, M, in_is_coords);
+  if (!force_fp32 && c.tc) {
+    forward_rows_tc(c, in, gather, goff, M, in_is_coords, keep);
     return;
   }
   if (!force_fp32 && c.tiny && !keep && gather == nullptr) {
@@ -185,11 +183,14 @@ void forward_rows(Ctx &c, const float *in, const int64_t *gather, int64_t goff, 
 // tensor-core path (wide nets): split-bf16 activations, tcgen05 GEMMs for layers 0..L-2, thin
 // kernels for the last layer
 // ------------------------------------------------------------------------------------------
-bool tc_eligible(const isokann_config &g) {
+// wide: every hidden layer is a real tensor-core GEMM (AUTO uses tcgen05 for everything);
+// any:  the tensor-core kernels can run the net at all (TMA zero-fills the padded tiles) -- used by AUTO for the
+//       large-minibatch training steps of narrow nets, where the FP32 CUDA-core GEMMs are latency-bound
+bool tc_eligible(const isokann_config &g, bool wide) {
   if (g.n_layers < 2) return false;
   if (g.widths[0] < 64 || g.widths[g.n_layers] > kMaxD) return false;
   for (int l = 1; l < g.n_layers; ++l)
-    if (g.widths[l] < 256) return false;
+    if (g.widths[l] < (wide ? 256 : 1)) return false;
   return true;
 }
 
@@ -205,7 +206,7 @@ bool tcn_eligible(const isokann_config &g) {
 void tc_ensure_rows(Ctx &c, int64_t rows) {
   TcState &t = *c.tcs;
   if (rows > t.rows) {
-    for (int l = 0; l < (c.tcn ? 1 : c.L); ++l) {
+    for (int l = 0; l < (c.tc ? c.L : 1); ++l) {
       t.act[l].ensure(rows, t.wp[l]);
       // column w_l := 1 once; the GEMM epilogues never touch it when w_l is a multiple of 32 and rewrite it otherwise
       if (l > 0) launch_set_ones_col(c, t.act[l].hi.p, t.act[l].lo.p, rows, t.wp[l], c.cfg.widths[l]);
@@ -219,7 +220,7 @@ void ensure_tc_weights(Ctx &c) {
   if (c.tc_weights_valid) return;
   ensure_folded(c);
   TcState &t = *c.tcs;
-  for (int l = 0; l + 1 < (c.tcn ? 2 : c.L); ++l) {
+  for (int l = 0; l + 1 < (c.tc ? c.L : 2); ++l) {
     const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
     t.wF[l].ensure(fout, t.wp[l]);
     if (l > 0) t.wD[l].ensure(fin, t.wp[l + 1]);
@@ -1030,11 +1031,11 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
       c->gfold.ensure(seg);
     }
     if (cfg->gemm_mode == ISOKANN_GEMM_TC)
-      IK_REQUIRE(tc_eligible(*cfg), ISOKANN_BAD_ARGUMENT,
+      IK_REQUIRE(tc_eligible(*cfg, true), ISOKANN_BAD_ARGUMENT,
                  "ISOKANN_GEMM_TC needs >= 2 layers, hidden widths >= 256, input width >= 64, output <= 8");
-    c->tc = cfg->gemm_mode != ISOKANN_GEMM_FP32 && tc_eligible(*cfg);
-    c->tcn = !c->tc && cfg->gemm_mode == ISOKANN_GEMM_AUTO && tcn_eligible(*cfg);
-    c->fused_train = !c->tc && cfg->gemm_mode == ISOKANN_GEMM_AUTO && narrow_train_eligible(*cfg);
+    c->tc = cfg->gemm_mode != ISOKANN_GEMM_FP32 && tc_eligible(*cfg, cfg->gemm_mode == ISOKANN_GEMM_TC);
+    c->tcn = cfg->gemm_mode == ISOKANN_GEMM_AUTO && !tc_eligible(*cfg, true) && tcn_eligible(*cfg);
+    c->fused_train = cfg->gemm_mode == ISOKANN_GEMM_AUTO && !tc_eligible(*cfg, true) && narrow_train_eligible(*cfg);
     c->tiny = cfg->gemm_mode == ISOKANN_GEMM_AUTO && tiny_forward_eligible(*cfg);
     if (c->tc || c->tcn) {
       c->tcs = new TcState;
