@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -1037,6 +1038,7 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
     c->tcn = cfg->gemm_mode == ISOKANN_GEMM_AUTO && !tc_eligible(*cfg, true) && tcn_eligible(*cfg);
     c->fused_train = cfg->gemm_mode == ISOKANN_GEMM_AUTO && !tc_eligible(*cfg, true) && narrow_train_eligible(*cfg);
     c->tiny = cfg->gemm_mode == ISOKANN_GEMM_AUTO && tiny_forward_eligible(*cfg);
+    c->tc_no_pair = getenv("ISOKANN_TC_NO_PAIR") != nullptr;
     if (c->tc || c->tcn) {
       c->tcs = new TcState;
       c->tcs->act.resize(c->L);

@@ -53,6 +53,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   uint32_t spins = 0;
+  long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -62,7 +63,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > 200000000u) __trap();  // try_wait suspends in hardware between probes
+    if ((++spins & 1023u) == 0) {  // try_wait suspends in hardware between probes; look at the clock rarely
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 6000000000LL) __trap();  // ~3 s: protocol bug, not a slow tile
+    }
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
@@ -176,6 +180,199 @@ struct TcParams {
   const __nv_bfloat16 *z_hi, *z_lo;  // EPI_MULDACT: activation outputs (split), leading dimension ldz
   int64_t ldz;
 };
+
+// Epilogue of one 128 x 256 accumulator for one warp (its 32 rows, one 128-column half): shared by the 1-CTA and
+// the 2-CTA kernels.  row0 is the first output row of this CTA's accumulator.
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const TcParams &p, uint32_t tmem_acc, int64_t row0, int nb, int split,
+                                              int quarter, int half, int lane, const float *tailw) {
+  const int64_t row = row0 + quarter * 32 + lane;
+  const bool row_ok = row < p.M;
+  const uint32_t taddr0 = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+  float dot[kMaxD];
+#pragma unroll
+  for (int a = 0; a < kMaxD; ++a) dot[a] = 0.f;
+  float tl[16];  // TC_EPI_TAIL: pre-activations of the first tail layer
+#pragma unroll
+  for (int a = 0; a < 16; ++a) tl[a] = 0.f;
+#pragma unroll 1
+  for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+    const int col0 = nb * BN + c;
+    if (col0 >= p.N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld32(taddr0 + c, r);
+    if (!row_ok) continue;
+    const bool full = col0 + 32 <= p.N;
+    if (EPI == TC_EPI_F32) {
+      float *dst = p.out_f32 + (int64_t)split * p.M * p.ldc + row * p.ldc + col0;
+      if (full && p.f32_vec) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4 *>(dst + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                          __uint_as_float(r[j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]);
+      }
+      continue;
+    }
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (EPI == TC_EPI_MULDACT_SPLIT) {
+      const uint4 *zh = reinterpret_cast<const uint4 *>(p.z_hi + row * p.ldz + col0);
+      const uint4 *zl = reinterpret_cast<const uint4 *>(p.z_lo + row * p.ldz + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 h = __ldg(zh + q), l = __ldg(zl + q);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float z0 = bf16lo(hw[e]) + bf16lo(lw[e]);
+          const float z1 = bf16hi(hw[e]) + bf16hi(lw[e]);
+          v[q * 8 + 2 * e] *= dact_o(z0, p.act);
+          v[q * 8 + 2 * e + 1] *= dact_o(z1, p.act);
+        }
+      }
+    } else {  // bias + activation
+      if (p.bias) {
+        if (full) {
+          const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0);
+          if ((reinterpret_cast<uintptr_t>(b4) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = __ldg(b4 + q);
+              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + col0 + j);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+        }
+      }
+      if (p.act == ISOKANN_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
+      } else if (p.act != ISOKANN_ACT_IDENTITY) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act);
+      }
+    }
+    if (EPI == TC_EPI_TAIL) {
+      // first tail layer: a[k] += z[col] * W[col, k] with W rows broadcast from shared memory
+      const int cp = (p.tail.w[1] + 3) & ~3;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (col0 + j < p.N) {
+          const float4 *wr = reinterpret_cast<const float4 *>(tailw + (col0 + j) * cp);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (4 * q < cp) {
+              const float4 w4 = wr[q];
+              tl[4 * q] = fmaf(v[j], w4.x, tl[4 * q]);
+              tl[4 * q + 1] = fmaf(v[j], w4.y, tl[4 * q + 1]);
+              tl[4 * q + 2] = fmaf(v[j], w4.z, tl[4 * q + 2]);
+              tl[4 * q + 3] = fmaf(v[j], w4.w, tl[4 * q + 3]);
+            }
+          }
+        }
+      }
+      continue;
+    }
+    if (EPI == TC_EPI_BIAS_ACT_DOT) {
+      // chi partial: sum over this warp's columns of z[col] * W_last[col, a]
+      if (p.d == 1 && full && ((reinterpret_cast<uintptr_t>(p.w_last + col0) & 15) == 0)) {
+        const float4 *w4 = reinterpret_cast<const float4 *>(p.w_last + col0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 w = __ldg(w4 + q);
+          dot[0] = fmaf(v[4 * q], w.x, dot[0]);
+          dot[0] = fmaf(v[4 * q + 1], w.y, dot[0]);
+          dot[0] = fmaf(v[4 * q + 2], w.z, dot[0]);
+          dot[0] = fmaf(v[4 * q + 3], w.w, dot[0]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (col0 + j < p.N) {
+            const float *wl = p.w_last + (int64_t)(col0 + j) * p.d;
+#pragma unroll
+            for (int a = 0; a < kMaxD; ++a)
+              if (a < p.d) dot[a] = fmaf(v[j], __ldg(wl + a), dot[a]);
+          }
+        }
+      }
+      continue;
+    }
+    if (!full) {  // columns >= N inside the padded leading dimension: zeros, except the bias column N
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j >= p.N) v[j] = (p.ones_col && col0 + j == p.N) ? 1.f : 0.f;
+    }
+    uint32_t ph[16], pl[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+    __nv_bfloat16 *dh = p.out_hi + row * p.ldo + col0;
+    __nv_bfloat16 *dl = p.out_lo + row * p.ldo + col0;
+    if (p.st_v8) {
+      st_global_v8(dh, ph);
+      st_global_v8(dh + 16, ph + 8);
+      st_global_v8(dl, pl);
+      st_global_v8(dl + 16, pl + 8);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        reinterpret_cast<uint4 *>(dh)[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+        reinterpret_cast<uint4 *>(dl)[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+      }
+    }
+  }
+  if (EPI == TC_EPI_TAIL && row_ok && half == 0) {
+    // finish the tail: bias + activation of its first layer, then the remaining (tiny) layers
+    int off = 0;
+    float h[16];
+    {
+      const int cols = p.tail.w[1], cp = (cols + 3) & ~3;
+      const float *brow = tailw + p.tail.w[0] * cp;
+      const int kind = p.tail.nl == 1 ? p.tail.last_act : p.tail.act;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) h[k] = k < cols ? act_fwd(tl[k] + brow[k], kind) : 0.f;
+      off += (p.tail.w[0] + 1) * cp;
+    }
+    for (int i = 1; i < p.tail.nl; ++i) {
+      const int rows = p.tail.w[i], cols = p.tail.w[i + 1], cp = (cols + 3) & ~3;
+      float a2[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a2[k] = k < cols ? tailw[off + rows * cp + k] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < rows) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (k < cp) a2[k] = fmaf(h[j], tailw[off + j * cp + k], a2[k]);
+        }
+      }
+      const int kind = i == p.tail.nl - 1 ? p.tail.last_act : p.tail.act;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) h[k] = k < cols ? act_fwd(a2[k], kind) : 0.f;
+      off += (rows + 1) * cp;
+    }
+    const int dd = p.tail.w[p.tail.nl];
+#pragma unroll
+    for (int k = 0; k < kMaxD; ++k)
+      if (k < dd) p.chi_out[row * dd + k] = h[k];
+  }
+  if (EPI == TC_EPI_BIAS_ACT_DOT && row_ok) {
+    float *dst = p.dot_out + (row * p.dot_slots + (nb * 2 + half)) * p.d;
+    for (int a = 0; a < p.d; ++a) dst[a] = dot[a];
+  }
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -328,192 +525,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const int64_t row = (int64_t)mb * BM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t taddr0 = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
-      float dot[kMaxD];
-#pragma unroll
-      for (int a = 0; a < kMaxD; ++a) dot[a] = 0.f;
-      float tl[16];  // TC_EPI_TAIL: pre-activations of the first tail layer
-#pragma unroll
-      for (int a = 0; a < 16; ++a) tl[a] = 0.f;
-#pragma unroll 1
-      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
-        const int col0 = nb * BN + c;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(taddr0 + c, r);
-        if (!row_ok) continue;
-        const bool full = col0 + 32 <= p.N;
-        if (EPI == TC_EPI_F32) {
-          float *dst = p.out_f32 + (int64_t)split * p.M * p.ldc + row * p.ldc + col0;
-          if (full && p.f32_vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4 *>(dst + j) =
-                  make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                              __uint_as_float(r[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]);
-          }
-          continue;
-        }
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (EPI == TC_EPI_MULDACT_SPLIT) {
-          const uint4 *zh = reinterpret_cast<const uint4 *>(p.z_hi + row * p.ldz + col0);
-          const uint4 *zl = reinterpret_cast<const uint4 *>(p.z_lo + row * p.ldz + col0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 h = __ldg(zh + q), l = __ldg(zl + q);
-            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float z0 = bf16lo(hw[e]) + bf16lo(lw[e]);
-              const float z1 = bf16hi(hw[e]) + bf16hi(lw[e]);
-              v[q * 8 + 2 * e] *= dact_o(z0, p.act);
-              v[q * 8 + 2 * e + 1] *= dact_o(z1, p.act);
-            }
-          }
-        } else {  // bias + activation
-          if (p.bias) {
-            if (full) {
-              const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + col0);
-              if ((reinterpret_cast<uintptr_t>(b4) & 15) == 0) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const float4 b = __ldg(b4 + q);
-                  v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + col0 + j);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-            }
-          }
-          if (p.act == ISOKANN_ACT_SIGMOID) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
-          } else if (p.act != ISOKANN_ACT_IDENTITY) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act);
-          }
-        }
-        if (EPI == TC_EPI_TAIL) {
-          // first tail layer: a[k] += z[col] * W[col, k] with W rows broadcast from shared memory
-          const int cp = (p.tail.w[1] + 3) & ~3;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < p.N) {
-              const float4 *wr = reinterpret_cast<const float4 *>(tailw + (col0 + j) * cp);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (4 * q < cp) {
-                  const float4 w4 = wr[q];
-                  tl[4 * q] = fmaf(v[j], w4.x, tl[4 * q]);
-                  tl[4 * q + 1] = fmaf(v[j], w4.y, tl[4 * q + 1]);
-                  tl[4 * q + 2] = fmaf(v[j], w4.z, tl[4 * q + 2]);
-                  tl[4 * q + 3] = fmaf(v[j], w4.w, tl[4 * q + 3]);
-                }
-              }
-            }
-          }
-          continue;
-        }
-        if (EPI == TC_EPI_BIAS_ACT_DOT) {
-          // chi partial: sum over this warp's columns of z[col] * W_last[col, a]
-          if (p.d == 1 && full && ((reinterpret_cast<uintptr_t>(p.w_last + col0) & 15) == 0)) {
-            const float4 *w4 = reinterpret_cast<const float4 *>(p.w_last + col0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 w = __ldg(w4 + q);
-              dot[0] = fmaf(v[4 * q], w.x, dot[0]);
-              dot[0] = fmaf(v[4 * q + 1], w.y, dot[0]);
-              dot[0] = fmaf(v[4 * q + 2], w.z, dot[0]);
-              dot[0] = fmaf(v[4 * q + 3], w.w, dot[0]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col0 + j < p.N) {
-                const float *wl = p.w_last + (int64_t)(col0 + j) * p.d;
-#pragma unroll
-                for (int a = 0; a < kMaxD; ++a)
-                  if (a < p.d) dot[a] = fmaf(v[j], __ldg(wl + a), dot[a]);
-              }
-            }
-          }
-          continue;
-        }
-        if (!full) {  // columns >= N inside the padded leading dimension: zeros, except the bias column N
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j >= p.N) v[j] = (p.ones_col && col0 + j == p.N) ? 1.f : 0.f;
-        }
-        uint32_t ph[16], pl[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
-        __nv_bfloat16 *dh = p.out_hi + row * p.ldo + col0;
-        __nv_bfloat16 *dl = p.out_lo + row * p.ldo + col0;
-        if (p.st_v8) {
-          st_global_v8(dh, ph);
-          st_global_v8(dh + 16, ph + 8);
-          st_global_v8(dl, pl);
-          st_global_v8(dl + 16, pl + 8);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            reinterpret_cast<uint4 *>(dh)[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-            reinterpret_cast<uint4 *>(dl)[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
-          }
-        }
-      }
-      if (EPI == TC_EPI_TAIL && row_ok && half == 0) {
-        // finish the tail: bias + activation of its first layer, then the remaining (tiny) layers
-        int off = 0;
-        float h[16];
-        {
-          const int cols = p.tail.w[1], cp = (cols + 3) & ~3;
-          const float *brow = tailw + p.tail.w[0] * cp;
-          const int kind = p.tail.nl == 1 ? p.tail.last_act : p.tail.act;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) h[k] = k < cols ? act_fwd(tl[k] + brow[k], kind) : 0.f;
-          off += (p.tail.w[0] + 1) * cp;
-        }
-        for (int i = 1; i < p.tail.nl; ++i) {
-          const int rows = p.tail.w[i], cols = p.tail.w[i + 1], cp = (cols + 3) & ~3;
-          float a2[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) a2[k] = k < cols ? tailw[off + rows * cp + k] : 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (j < rows) {
-#pragma unroll
-              for (int k = 0; k < 16; ++k)
-                if (k < cp) a2[k] = fmaf(h[j], tailw[off + j * cp + k], a2[k]);
-            }
-          }
-          const int kind = i == p.tail.nl - 1 ? p.tail.last_act : p.tail.act;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) h[k] = k < cols ? act_fwd(a2[k], kind) : 0.f;
-          off += (rows + 1) * cp;
-        }
-        const int dd = p.tail.w[p.tail.nl];
-#pragma unroll
-        for (int k = 0; k < kMaxD; ++k)
-          if (k < dd) p.chi_out[row * dd + k] = h[k];
-      }
-      if (EPI == TC_EPI_BIAS_ACT_DOT && row_ok) {
-        float *dst = p.dot_out + (row * p.dot_slots + (nb * 2 + half)) * p.d;
-        for (int a = 0; a < p.d; ++a) dst[a] = dot[a];
-      }
+      epilogue_tile<EPI>(p, tmem_base + acc * BN, (int64_t)mb * BM, nb, split, quarter, half, lane, tailw);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -525,6 +537,196 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a pair of CTAs on neighbouring SMs computes one 256 x 256 tile.  Each CTA loads its
+// own 128 rows of A and HALF of the B tile (128 of the 256 N rows); the leader CTA issues tcgen05.mma with M = 256
+// and the tensor cores of both SMs read both halves, so the B operand crosses L2 -> SMEM once per pair: 64 KiB
+// instead of 96 KiB per CTA and k-block (3 stages fit).  Barrier protocol:
+//   full[s]    leader only: its producer arms 2 x 64 KiB; both CTAs' TMA loads complete_tx on the LEADER's barrier
+//   empty[s]   both CTAs: tcgen05.commit ... multicast::cluster arrives on both when the MMAs have read stage s
+//   tfull[a]   both CTAs: multicast commit when the accumulator is complete (each CTA drains its own TMEM)
+//   tempty[a]  leader only: 2 x 8 epilogue warps arrive (the peer's through mapa / shared::cluster)
+// ------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 3;
+constexpr int B2_TILE = (BN / 2) * BK * 2;
+constexpr int STAGE2_BYTES = 2 * A_TILE + 2 * B2_TILE;  // 64 KiB per CTA
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      :
+      : "r"(local_bar), "r"(cta)
+      : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *base_ptr = smem_raw + (base - raw);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(base_ptr + STAGES2 * STAGE2_BYTES);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * STAGES2;
+  const uint32_t bar_tfull = bar_empty + 8 * STAGES2, bar_tempty = bar_tfull + 16;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES2 + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_tiles2 = (p.M + 2 * BM - 1) / (2 * BM);
+  const int total_tiles = m_tiles2 * p.n_tiles;
+  const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 2 * EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = cl; t < total_tiles; t += ncl) {
+        const int mb2 = t / p.n_tiles, nb = t - mb2 * p.n_tiles;
+        const int m0 = mb2 * 2 * BM + (int)rank * BM;
+        const int n0 = nb * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = base + stage * STAGE2_BYTES;
+          const uint32_t full_local = bar_full + 8 * stage;
+          const uint32_t full_leader = full_local & 0xFEFFFFFFu;  // peer bit cleared: the even CTA of the pair
+          if (leader) mbar_arrive_expect_tx(full_local, 2 * STAGE2_BYTES);
+          tma_load_2d_cg2(sa, &map_ah, full_leader, kb * BK, m0);
+          tma_load_2d_cg2(sa + A_TILE, &map_al, full_leader, kb * BK, m0);
+          tma_load_2d_cg2(sa + 2 * A_TILE, &map_bh, full_leader, kb * BK, n0);
+          tma_load_2d_cg2(sa + 2 * A_TILE + B2_TILE, &map_bl, full_leader, kb * BK, n0);
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      // D=f32, A=B=bf16, K-major, N=256, M=256 (2 x 128 across the CTA pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int t = cl; t < total_tiles; t += ncl, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * STAGE2_BYTES;
+          const uint64_t dah = make_desc_sw128(sa), dal = make_desc_sw128(sa + A_TILE);
+          const uint64_t dbh = make_desc_sw128(sa + 2 * A_TILE), dbl = make_desc_sw128(sa + 2 * A_TILE + B2_TILE);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            umma2_f16(tmem_d, dah + adv, dbh + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma2_f16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+            umma2_f16(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+          }
+          umma_commit_mc(bar_empty + 8 * stage);
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_mc(bar_tfull + 8 * acc);
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int it = 0;
+    for (int t = cl; t < total_tiles; t += ncl, ++it) {
+      const int mb2 = t / p.n_tiles, nb = t - mb2 * p.n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      epilogue_tile<EPI>(p, tmem_base + acc * BN, (int64_t)mb2 * 2 * BM + (int64_t)rank * BM, nb, 0, quarter, half, lane,
+                         nullptr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(bar_tempty + 8 * acc);
+        else mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -630,6 +832,38 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
       fl += (g.tail.w[i] + 1) * ((g.tail.w[i + 1] + 3) & ~3);
     }
     IK_REQUIRE(fl <= TAIL_FLOATS && g.tail.w[g.tail.nl] <= kMaxD, ISOKANN_BAD_ARGUMENT, "tail too large");
+  }
+  // 2-CTA pairs for the large K-major GEMMs (forward / data gradient): B crosses L2 -> SMEM once per pair
+  const int m_tiles2 = cdiv(g.M, 2 * BM);
+  const bool pair = !g.mn_major && g.epi != TC_EPI_F32 && g.epi != TC_EPI_TAIL && g.N > BN / 2 &&
+                    m_tiles2 * p.n_tiles >= c.num_sms / 2 && !c.tc_no_pair;
+  if (pair) {
+    static bool attr2 = false;
+    if (!attr2) {
+      IK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_EPI_BIAS_ACT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      IK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_EPI_MULDACT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      IK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_EPI_BIAS_ACT_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      attr2 = true;
+    }
+    make_map(&mbh, g.b_hi, g.N, g.K, g.ldb, BN / 2);  // each CTA of the pair loads half of the B tile
+    make_map(&mbl, g.b_lo, g.N, g.K, g.ldb, BN / 2);
+    const int grid2 = 2 * std::min(m_tiles2 * p.n_tiles, c.num_sms / 2);
+    c.timer.begin(KC_GEMM, c.stream);
+    switch (g.epi) {
+      case TC_EPI_BIAS_ACT_SPLIT:
+        tc_gemm2_kernel<TC_EPI_BIAS_ACT_SPLIT><<<grid2, NTHREADS, SMEM2_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);
+        break;
+      case TC_EPI_MULDACT_SPLIT:
+        tc_gemm2_kernel<TC_EPI_MULDACT_SPLIT><<<grid2, NTHREADS, SMEM2_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);
+        break;
+      default:
+        tc_gemm2_kernel<TC_EPI_BIAS_ACT_DOT><<<grid2, NTHREADS, SMEM2_BYTES, c.stream>>>(mah, mal, mbh, mbl, p);
+        break;
+    }
+    c.timer.end(c.stream);
+    IK_CUDA(cudaGetLastError());
+    c.count_launch(KC_GEMM, 2.0 * (double)g.M * (double)g.N * (double)g.K);
+    return 1;
   }
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = std::min(total, c.num_sms);

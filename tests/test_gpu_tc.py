@@ -94,3 +94,13 @@ def test_tc_mode_rejects_narrow_nets(pkg):
     model = pkg.pairnet(n=231)
     with pytest.raises(pkg.IsokannError):
         pkg.Engine(model, pkg.NesterovRegularized(), "allpairs", 22, gemm="tc")
+
+
+def test_tc_two_cta_kernel(pkg, oracle):
+    # large enough for the cta_group::2 kernel (>= 74 tile pairs): forward (split + fused-dot epilogues) and a
+    # full-batch training step (data-gradient GEMM) against the oracle
+    r = run_pair(pkg, oracle, "c1", N=40000, K=1, minibatch=0, n_iter=1, opt="adam", gemm="tc",
+                 widths=[231, 264, 512, 1])
+    assert np.allclose(r["chi0_lib"], r["chi0_ref"], rtol=TOL_CHI, atol=5e-5)
+    assert np.allclose(r["loss_lib"], r["loss_ref"], rtol=2e-3)
+    assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=1e-3, atol=1e-3)
