@@ -1087,8 +1087,6 @@ int32_t isokann_destroy(isokann_ctx *c) {
     for (auto &b : c->tcs->act) b.release();
     for (auto &b : c->tcs->wF) b.release();
     for (auto &b : c->tcs->wD) b.release();
-    c->tcs->actT.release();
-    c->tcs->deltaT.release();
     c->tcs->delta[0].release();
     c->tcs->delta[1].release();
     c->tcs->dot_partial.release();

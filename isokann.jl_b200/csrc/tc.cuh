@@ -66,7 +66,6 @@ struct TcState {
   std::vector<SplitBuf> act;   // act[l], l = 0..L-1: row-major rows x wp_l
   std::vector<SplitBuf> wF;    // forward operand of layer l (l = 0..L-2): [w_{l+1} x wp_l]
   std::vector<SplitBuf> wD;    // dgrad operand of layer l   (l = 1..L-2): [w_l x wp_{l+1}]
-  SplitBuf actT, deltaT;       // transposed activation (+ ones row) / delta of the current layer
   SplitBuf delta[2];           // row-major delta ping-pong
   SplitBuf dlast;              // split copy of the last layer's delta (B x d, padded to 64 columns)
   DevBuf<float> dot_partial;   // fused last layer: partial chi per 128-column slot
@@ -82,10 +81,6 @@ void launch_f32_to_split(Ctx &c, const float *in, int64_t rows, int cols, __nv_b
                          int64_t ld);
 // set column `col` of a split matrix to (hi, lo) = (1, 0) for every row
 void launch_set_ones_col(Ctx &c, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t rows, int64_t ld, int col);
-// [rows x cols] split (ld_in) -> transposed [cols(+ones row) x ld_out] split; columns >= rows are zero
-void launch_transpose_split(Ctx &c, const __nv_bfloat16 *in_hi, const __nv_bfloat16 *in_lo, int64_t rows, int cols,
-                            int64_t ld_in, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld_out,
-                            bool ones_row);
 // weights of one Dense layer: flat fp32 segment seg[(in) x out] (row-major) ->
 //   fwd operand  Wf[out x ld_f] (K = in contiguous) and dgrad operand Wd[in x ld_d] (K = out contiguous)
 void launch_prep_weights(Ctx &c, const float *seg, int fin, int fout, __nv_bfloat16 *wf_hi, __nv_bfloat16 *wf_lo,
@@ -100,8 +95,5 @@ void launch_thin_dgrad(Ctx &c, const float *delta, int64_t M, int d, const float
 // chi[m, a] = act(sum_s partial[m, s, a] + b[a]) -- finishes the fused last layer
 void launch_dot_finish(Ctx &c, const float *partial, int64_t M, int slots, int d, const float *bias, int act,
                        float *chi);
-// grad[(fin+1) x d] = [z, 1]^T * delta from the transposed split activation zT[(fin+1) x ldt]
-void launch_thin_wgrad(Ctx &c, const __nv_bfloat16 *zt_hi, const __nv_bfloat16 *zt_lo, int64_t ldt, int fin, int64_t M,
-                       const float *delta, int d, float *grad);
 
 }  // namespace ik

@@ -1,4 +1,4 @@
-// Kernels around the tcgen05 GEMM: operand preparation (fp32 -> bf16 hi/lo split, transposes)
+// Kernels around the tcgen05 GEMM: operand preparation (fp32 -> bf16 hi/lo split, weight layouts)
 // and the thin last Dense layer (out = d <= 8), which is a memory-bound row reduction rather
 // than a GEMM.  All of them are HBM-bound passes with 16-byte vector accesses.
 #include "tc.cuh"
@@ -27,48 +27,6 @@ __device__ __forceinline__ float dact_f(float z, int kind) {
     case ISOKANN_ACT_TANH: return 1.0f - z * z;
     case ISOKANN_ACT_RELU: return z > 0.f ? 1.0f : 0.f;
     default: return 1.0f;
-  }
-}
-
-// ---- 64x64 tile transpose of a split matrix ----
-__global__ void __launch_bounds__(256) transpose_split_kernel(const __nv_bfloat16 *__restrict__ in_hi,
-                                                              const __nv_bfloat16 *__restrict__ in_lo, int64_t rows,
-                                                              int cols, int64_t ld_in,
-                                                              __nv_bfloat16 *__restrict__ out_hi,
-                                                              __nv_bfloat16 *__restrict__ out_lo, int64_t ld_out,
-                                                              int ones_row) {
-  __shared__ __nv_bfloat16 th[64][66], tl[64][66];
-  const int64_t r0 = (int64_t)blockIdx.x * 64;
-  const int c0 = blockIdx.y * 64;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
-  for (int i = ty; i < 64; i += 4) {
-    const int64_t r = r0 + i;
-    const int cc = c0 + tx;
-    __nv_bfloat16 h = __float2bfloat16_rn(0.f), l = h;
-    if (r < rows && cc < cols) {
-      h = in_hi[r * ld_in + cc];
-      l = in_lo[r * ld_in + cc];
-    }
-    th[i][tx] = h;
-    tl[i][tx] = l;
-  }
-  __syncthreads();
-  for (int i = ty; i < 64; i += 4) {
-    const int cc = c0 + i;       // output row
-    const int64_t r = r0 + tx;   // output column
-    if (cc < cols && r < rows) {
-      out_hi[(int64_t)cc * ld_out + r] = th[tx][i];
-      out_lo[(int64_t)cc * ld_out + r] = tl[tx][i];
-    }
-  }
-  if (ones_row && blockIdx.y == 0) {
-    for (int i = threadIdx.x; i < 64; i += 256) {
-      const int64_t r = r0 + i;
-      if (r < rows) {
-        out_hi[(int64_t)cols * ld_out + r] = __float2bfloat16_rn(1.0f);
-        out_lo[(int64_t)cols * ld_out + r] = __float2bfloat16_rn(0.0f);
-      }
-    }
   }
 }
 
@@ -200,39 +158,6 @@ __global__ void __launch_bounds__(256) thin_dgrad_kernel(const float *__restrict
   }
 }
 
-// ---- thin wgrad: one block per row k of zT (row fin = ones -> bias gradient) ----
-__global__ void __launch_bounds__(256) thin_wgrad_kernel(const __nv_bfloat16 *__restrict__ zt_hi,
-                                                         const __nv_bfloat16 *__restrict__ zt_lo, int64_t ldt,
-                                                         int64_t M, const float *__restrict__ delta, int d,
-                                                         float *__restrict__ grad) {
-  __shared__ float sh[8][kMaxD];
-  const int k = blockIdx.x;
-  float acc[kMaxD];
-#pragma unroll
-  for (int a = 0; a < kMaxD; ++a) acc[a] = 0.f;
-  const __nv_bfloat16 *ph = zt_hi + (int64_t)k * ldt, *pl = zt_lo + (int64_t)k * ldt;
-  for (int64_t m = threadIdx.x; m < M; m += blockDim.x) {
-    const float z = __bfloat162float(ph[m]) + __bfloat162float(pl[m]);
-#pragma unroll
-    for (int a = 0; a < kMaxD; ++a)
-      if (a < d) acc[a] = fmaf(z, __ldg(delta + m * d + a), acc[a]);
-  }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int a = 0; a < kMaxD; ++a) {
-    float s = acc[a];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sh[w][a] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < d) {
-    float s = 0.f;
-    for (int ww = 0; ww < 8; ++ww) s += sh[ww][threadIdx.x];
-    grad[(int64_t)k * d + threadIdx.x] = s;
-  }
-}
-
 __global__ void f32_to_split_kernel(const float *__restrict__ in, int64_t rows, int cols, __nv_bfloat16 *hi,
                                     __nv_bfloat16 *lo, int64_t ld) {
   const int64_t total = rows * ld;
@@ -298,19 +223,6 @@ void launch_dot_finish(Ctx &c, const float *partial, int64_t M, int slots, int d
   c.count_launch(KC_REDUCE);
 }
 
-void launch_transpose_split(Ctx &c, const __nv_bfloat16 *in_hi, const __nv_bfloat16 *in_lo, int64_t rows, int cols,
-                            int64_t ld_in, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld_out,
-                            bool ones_row) {
-  if (rows <= 0) return;
-  dim3 grid(cdiv(rows, 64), cdiv(cols, 64));
-  c.timer.begin(KC_TRAIN_EW, c.stream);
-  transpose_split_kernel<<<grid, 256, 0, c.stream>>>(in_hi, in_lo, rows, cols, ld_in, out_hi, out_lo, ld_out,
-                                                     ones_row ? 1 : 0);
-  c.timer.end(c.stream);
-  IK_CUDA(cudaGetLastError());
-  c.count_launch(KC_TRAIN_EW);
-}
-
 void launch_prep_weights(Ctx &c, const float *seg, int fin, int fout, __nv_bfloat16 *wf_hi, __nv_bfloat16 *wf_lo,
                          int64_t ld_f, __nv_bfloat16 *wd_hi, __nv_bfloat16 *wd_lo, int64_t ld_d) {
   dim3 grid(cdiv(fin, 64), cdiv(fout, 64));
@@ -341,15 +253,6 @@ void launch_thin_dgrad(Ctx &c, const float *delta, int64_t M, int d, const float
   int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c.num_sms * 16);
   c.timer.begin(KC_TRAIN_EW, c.stream);
   thin_dgrad_kernel<<<grid, 256, 0, c.stream>>>(delta, M, d, seg, fin, z_hi, z_lo, ldz, act, out_hi, out_lo, ldo);
-  c.timer.end(c.stream);
-  IK_CUDA(cudaGetLastError());
-  c.count_launch(KC_TRAIN_EW);
-}
-
-void launch_thin_wgrad(Ctx &c, const __nv_bfloat16 *zt_hi, const __nv_bfloat16 *zt_lo, int64_t ldt, int fin, int64_t M,
-                       const float *delta, int d, float *grad) {
-  c.timer.begin(KC_TRAIN_EW, c.stream);
-  thin_wgrad_kernel<<<fin + 1, 256, 0, c.stream>>>(zt_hi, zt_lo, ldt, M, delta, d, grad);
   c.timer.end(c.stream);
   IK_CUDA(cudaGetLastError());
   c.count_launch(KC_TRAIN_EW);

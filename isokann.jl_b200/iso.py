@@ -156,6 +156,24 @@ def propchis(iso: Iso) -> np.ndarray:
     return iso.engine.chis_prop()
 
 
+def validationloss(iso: Iso, valdata: SimulationData) -> float:
+    """validationloss(iso, valdata) (src/iso.jl:160-168): mean squared difference between chi on the validation
+    start points and the shift-scaled Koopman expectation, the shift-scale being estimated on validation and
+    training Koopman values together"""
+    vx, vy = valdata.coords
+    c = iso.engine.forward(vx).ravel()
+    D, K, Nv = vy.shape
+    k1 = iso.engine.forward(vy.reshape(D, K * Nv, order="F")).reshape(K, Nv, order="F")
+    k1 = k1.astype(np.float32).sum(axis=0) / np.float32(K)
+    k2 = koopman(iso).ravel()
+    both = np.concatenate([k1, k2])
+    lo, hi = both.min(), both.max()
+    if not hi > lo:
+        raise DomainError(1, "Could not compute the shift-scale. chi function is constant")
+    skc = ((both - lo) / (hi - lo))[:c.size]
+    return float(np.mean((c - skc) ** 2))
+
+
 def koopman(iso: Iso) -> np.ndarray:
     """koopman(iso) = expectation(model, propfeatures(data)) (src/isotarget.jl:20)"""
     return iso.engine.koopman()
@@ -194,6 +212,6 @@ def load_state(path: str, iso: Iso) -> Iso:
     return iso
 
 
-__all__ = ["Iso", "dchidx", "dchidfeat", "addcoords_", "cutoff_", "propchis", "run_", "train_batch_", "isotarget", "chis", "chicoords", "koopman", "chi_kchi", "cpu", "save",
+__all__ = ["Iso", "validationloss", "dchidx", "dchidfeat", "addcoords_", "cutoff_", "propchis", "run_", "train_batch_", "isotarget", "chis", "chicoords", "koopman", "chi_kchi", "cpu", "save",
            "load_state", "defaultmodel", "draw_perm", "DomainError", "TransformShiftscale", "TransformISA",
            "TransformPseudoInv"]

@@ -181,6 +181,29 @@ function train_batch!(m::B200Model, xs, target::AbstractMatrix, opt, minibatch; 
     loss[]
 end
 
+# dchidx(iso, x) (src/utils/minimumpath.jl:3-7): the Zygote pullback through chicoords is one library call
+function ISOKANN.dchidx(iso::Iso{<:B200Model}, x::AbstractVecOrMat)
+    m = iso.model
+    xf = Float32.(x); M = length(xf) ÷ size(xf, 1)
+    out = similar(xf)
+    check(m, ccall((:isokann_chi_vjp, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, Int64, Int64, Int32, Ptr{Float32}, Ptr{Float32}),
+        m.handle, xf, size(xf, 1), M, 0, C_NULL, out))
+    out
+end
+
+# addcoords!(iso, coords) (src/iso.jl:238): propagate on the host as before, upload only the new block
+function ISOKANN.addcoords!(iso::Iso{<:B200Model}, coords::AbstractMatrix)
+    new = SimulationData(iso.data.sim, coords, ISOKANN.nk(iso.data), featurizer=iso.data.featurizer)
+    xs, ys = Float32.(new.coords[1]), Float32.(new.coords[2])
+    check(iso.model, ccall((:isokann_append_data, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64, Int64, Int64),
+        iso.model.handle, xs, ys, size(ys, 1), size(ys, 2), size(ys, 3)))
+    iso.model.N += size(xs, 2)
+    iso.data = ISOKANN.mergedata(iso.data, new)
+    nothing
+end
+
 """run!(iso, n, epochs) without host round trips (src/iso.jl:72-94)"""
 function run_fused!(iso::Iso{<:B200Model}, n=1, epochs=1)
     m = iso.model

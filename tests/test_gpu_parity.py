@@ -431,3 +431,18 @@ def test_append_cutoff_and_propchis(pkg, oracle):
     assert np.array_equal(pkg.koopman(grown), pkg.koopman(tail))
     with pytest.raises(pkg.IsokannError):                               # the old target no longer matches the data
         pkg.train_batch_(grown, np.arange(1, 101))
+
+
+def test_validationloss(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    xs, ys = pkg.synthetic.make_data(w, 200, 4)
+    om = oracle_model(oracle, w.widths, True, 5)
+    iso = make_iso(pkg, w, xs[:, :150], ys[:, :, :150], oracle.flatten_params(om))
+    val = pkg.SimulationData(xs[:, 150:], ys[:, :, 150:], featurizer=pkg.FeaturesAll())
+    got = pkg.validationloss(iso, val)
+    xsf, ysf = oracle_features(oracle, w, xs, ys)
+    c = oracle.forward(om, xsf[150:]).ravel()
+    k1 = oracle.expectation(om, ysf[150:]).ravel()
+    k2 = oracle.expectation(om, ysf[:150]).ravel()
+    skc = oracle.shiftscale(np.concatenate([k1, k2]))[:50]
+    assert np.isclose(got, np.mean((c - skc) ** 2), rtol=2e-3)
