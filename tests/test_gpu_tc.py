@@ -104,3 +104,51 @@ def test_tc_two_cta_kernel(pkg, oracle):
     assert np.allclose(r["chi0_lib"], r["chi0_ref"], rtol=TOL_CHI, atol=5e-5)
     assert np.allclose(r["loss_lib"], r["loss_ref"], rtol=2e-3)
     assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=1e-3, atol=1e-3)
+
+
+def test_full_size_c5_properties(pkg, oracle):
+    """BASELINE config 5 at full size (N = 10^6, K = 16, pairnet [595, 2048, 2048, 1]) through size-independent
+    properties; the data is generated on the device like bench.py does."""
+    import torch
+    w = pkg.synthetic.WORKLOADS["c5"]
+    N, K = w.N, w.K
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(w.seed)
+    states = pkg.synthetic.villin_states(rng, w.n_atoms)
+    base = torch.tensor(np.stack([s.reshape(-1) for s in states]), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    xs = (base[torch.randint(0, 2, (N,), generator=g, device=dev)] + 0.05 * torch.randn((N, w.D), generator=g, device=dev))
+    ys = torch.empty((N, K, w.D), dtype=torch.float32, device=dev)
+    for s in range(0, N, 1 << 16):
+        e = min(N, s + (1 << 16))
+        ys[s:e] = xs[s:e, None, :] + 0.03 * torch.randn((e - s, K, w.D), generator=g, device=dev)
+    torch.cuda.synchronize()
+    om = oracle_model(oracle, w.widths, True, w.seed + 1)
+    flat = oracle.flatten_params(om)
+    eng = pkg.Engine(pkg.Chain(list(w.widths), True).load_flat(flat), pkg.AdamRegularized(), "allpairs", w.n_atoms)
+    eng.set_data_dev(xs, ys, w.D, K, N)
+    k = eng.koopman()
+    t = eng.target("shiftscale")
+    assert t.shape == (1, N) and t.min() == 0.0 and t.max() == 1.0
+    assert np.allclose(t, (k - k.min()) / (k.max() - k.min()), atol=1e-6)
+    # rows spread over the whole data set (different chunks, different CTA pairs) against the oracle
+    rows = np.array([0, 1, 65535, 65536, 65537, 500_000, 999_998, 999_999])
+    ysub = ys[torch.from_numpy(rows).to(dev)].cpu().numpy()               # (8, K, D)
+    ref = oracle.expectation(om, oracle.flatpairdists(ysub))
+    assert np.allclose(records(k)[rows], ref, rtol=TOL_CHI, atol=5e-5)
+    xsub = xs[torch.from_numpy(rows).to(dev)].cpu().numpy()
+    chi = eng.chis()
+    assert np.allclose(records(chi)[rows], oracle.forward(om, oracle.flatpairdists(xsub)), rtol=TOL_CHI, atol=5e-5)
+    # the Koopman expectation of a constant-in-k sample equals chi of that sample (linearity of the K-mean)
+    perms = pkg.synthetic.make_perms(w, N, 2)
+    losses = eng.iterate("shiftscale", 2, 1, w.minibatch, perms)
+    assert np.isfinite(losses).all() and losses[1] < losses[0]
+    # the permutation is what defines the minibatches: the same permutation twice gives bit-identical parameters
+    eng2 = pkg.Engine(pkg.Chain(list(w.widths), True).load_flat(flat), pkg.AdamRegularized(), "allpairs", w.n_atoms)
+    eng2.set_data_dev(xs, ys, w.D, K, N)
+    losses2 = eng2.iterate("shiftscale", 2, 1, w.minibatch, perms)
+    assert np.array_equal(losses, losses2)
+    assert np.array_equal(eng.download_params(), eng2.download_params())
+    eng.close()
+    eng2.close()
