@@ -446,3 +446,56 @@ def test_validationloss(pkg, oracle):
     k2 = oracle.expectation(om, ysf[:150]).ravel()
     skc = oracle.shiftscale(np.concatenate([k1, k2]))[:50]
     assert np.isclose(got, np.mean((c - skc) ** 2), rtol=2e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------
+def test_edge_cases_small_and_empty(pkg, oracle):
+    w = pkg.synthetic.WORKLOADS["c1"]
+    xs, ys = pkg.synthetic.make_data(w, 50, 1)                      # K = 1, N < minibatch
+    om = oracle_model(oracle, w.widths, True, 5)
+    flat = oracle.flatten_params(om)
+    xsf, ysf = oracle_features(oracle, w, xs, ys)
+    perm = pkg.synthetic.make_perms(w, 50, 1)[0]
+    for mb in (100, 0, 50, 7):                                      # N < B, full batch, B == N, ragged tail
+        iso = make_iso(pkg, w, xs, ys, flat, minibatch=mb)
+        pkg.isotarget(iso)
+        loss = pkg.train_batch_(iso, perm)
+        m = om.copy()
+        cfg = oracle.OptConfig()
+        t = oracle.isotarget_shiftscale(m, xsf, ysf)
+        ref = oracle.train_batch(m, xsf, t, cfg, oracle.opt_init(cfg, flat.size), mb, perm)
+        assert np.isclose(loss, ref, rtol=1e-4), (mb, loss, ref)
+        assert np.abs(iso.engine.download_params() - oracle.flatten_params(m)).max() < 1e-5
+    # empty inputs
+    iso = make_iso(pkg, w, xs, ys, flat)
+    assert pkg.chicoords(iso, np.zeros((66, 0), np.float32)).shape == (1, 0)
+    assert pkg.flatpairdists(np.zeros((66, 0), np.float32)).shape == (231, 0)
+    assert pkg.dchidx(iso, np.zeros((66, 0), np.float32)).shape == (66, 0)
+    # a single record
+    one = pkg.chicoords(iso, xs[:, 3])
+    assert np.allclose(one, pkg.chis(iso)[:, 3], rtol=1e-5, atol=1e-6)
+    # wrong shapes are rejected, not mis-read
+    with pytest.raises(pkg.IsokannError):
+        iso.engine.forward(np.zeros((65, 4), np.float32))
+    with pytest.raises(pkg.IsokannError):
+        iso.engine.train_epoch(perm, -1)
+
+
+def test_wide_chi_dimension_and_limits(pkg, oracle):
+    w = copy.deepcopy(pkg.synthetic.WORKLOADS["c4"])
+    w.widths = [231, 38, 12, 8]                                     # d = 8 is the largest N-D target size
+    xs, ys = pkg.synthetic.make_data(w, 300, 2)
+    om = oracle_model(oracle, w.widths, True, 21)
+    iso = make_iso(pkg, w, xs, ys, oracle.flatten_params(om), target="isa", target_opts={"permute": False})
+    t = records(pkg.isotarget(iso))
+    xsf, ysf = oracle_features(oracle, w, xs, ys)
+    ref = oracle.isotarget("isa", om, xsf, ysf, permute=False)
+    assert np.allclose(t, ref, rtol=5e-3, atol=5e-3 * np.abs(ref).max())
+    w.widths = [231, 38, 12, 9]                                     # d = 9: N-D targets refuse, forward still works
+    om9 = oracle_model(oracle, w.widths, True, 22)
+    iso9 = make_iso(pkg, w, xs, ys, oracle.flatten_params(om9), target="isa")
+    assert np.allclose(records(pkg.chis(iso9)), oracle.forward(om9, xsf), rtol=TOL_CHI, atol=1e-5)
+    with pytest.raises(pkg.IsokannError):
+        pkg.isotarget(iso9)
