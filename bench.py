@@ -372,7 +372,7 @@ def run_b200(args, pkg):
                               "train": st["ms_train_total"] / nsteps},
         "kernel_ms_per_step": {"featurize": st["ms_featurize"] / nsteps, "gemm": st["ms_gemm"] / nsteps,
                                "reduce": st["ms_reduce"] / nsteps, "train_elementwise": st["ms_train_elementwise"] / nsteps,
-                               "optimiser": st["ms_optimiser"] / nsteps},
+                               "optimiser": st["ms_optimiser"] / nsteps, "nccl_allreduce": st["ms_nccl"] / nsteps},
     }
     if not args.no_cpu_baseline and world == 1:
         Ns = cpu_sample_size(w, N, K, args.cpu_sample)

@@ -111,6 +111,7 @@ typedef struct {
   int64_t n_featurize_launches;
   double gemm_flops;         /* algorithmic 2*M*N*K of the GEMMs timed in ms_gemm             */
   double featurize_bytes;    /* algorithmic 4*(D+F)*M of the launches timed in ms_featurize   */
+  double ms_nccl;            /* gradient all-reduces (includes waiting for the slowest rank)  */
 } isokann_stats;
 
 int32_t isokann_abi_version(void);

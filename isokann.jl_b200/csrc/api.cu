@@ -344,7 +344,8 @@ void backward_tc(Ctx &c, int64_t Bloc) {
     w.epi = TC_EPI_F32; w.act = ISOKANN_ACT_IDENTITY;
     w.ldc = fout;
     const int tiles = cdiv(w.M, 128) * cdiv(w.N, 256);
-    int splits = std::max(1, std::min((c.num_sms + tiles / 2) / tiles, (int)(Bloc / 2048)));
+    // as many split-K slices as fit in ONE wave of CTAs (a partial second wave would double the kernel time)
+    int splits = std::max(1, std::min(c.num_sms / tiles, (int)(Bloc / 2048)));
     if (splits > 1) {
       c.splitk.ensure((size_t)splits * w.M * w.N);
       w.out_f32 = c.splitk.p;
@@ -778,7 +779,9 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
   }
   if (c.world > 1) {
     std::string err;
+    c.timer.begin(KC_NCCL, c.stream);
     int rc = nccl_allreduce_sum_f32(c.nccl, c.comm, c.grads.p, (size_t)c.P + 2, c.stream, err);
+    c.timer.end(c.stream);
     IK_REQUIRE(rc == ISOKANN_OK, ISOKANN_ERR_NCCL, err);
     c.stats.nccl_calls++;
   }
@@ -1532,6 +1535,7 @@ int32_t isokann_get_stats(isokann_ctx *c, isokann_stats *out) {
     c->stats.ms_koopman_total = c->timer.ms[KC_PHASE_KOOPMAN];
     c->stats.ms_target_total = c->timer.ms[KC_PHASE_TARGET];
     c->stats.ms_train_total = c->timer.ms[KC_PHASE_TRAIN];
+    c->stats.ms_nccl = c->timer.ms[KC_NCCL];
     *out = c->stats;
   });
 }

@@ -35,7 +35,7 @@ enum : int { FLAG_CONSTANT_CHI = 1, FLAG_NONFINITE_LOSS = 2 };
 // kernel classes for the event timers
 enum KClass {
   KC_FEATURIZE = 0, KC_GEMM = 1, KC_REDUCE = 2, KC_TRAIN_EW = 3, KC_OPT = 4,
-  KC_PHASE_KOOPMAN = 5, KC_PHASE_TARGET = 6, KC_PHASE_TRAIN = 7, KC_COUNT = 8
+  KC_PHASE_KOOPMAN = 5, KC_PHASE_TARGET = 6, KC_PHASE_TRAIN = 7, KC_NCCL = 8, KC_COUNT = 9
 };
 
 struct EventTimer {
@@ -47,7 +47,7 @@ struct EventTimer {
   std::vector<Pair> pool;
   size_t used = 0;
   std::vector<size_t> open;
-  double ms[KC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double ms[KC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   void begin(int cls, cudaStream_t s);  // pairs may nest (phase around kernels)
   void end(cudaStream_t s);
   void flush(cudaStream_t s);  // synchronises the stream and accumulates elapsed times
