@@ -141,7 +141,7 @@ void ensure_folded(Ctx &c) {
 // featurize (+ parameter-free LayerNorm) M records and run all Dense layers; results stay in
 // c.act[0..L] (row-major M x width).  `in` holds coordinate records (in_is_coords) or features.
 void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords,
-                     bool keep);
+                     bool keep, const SplitBuf *x_pre = nullptr);
 void forward_rows_tcn(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords);
 
 // keep: the backward pass will need every layer's activations (training step)
@@ -231,19 +231,21 @@ void ensure_tc_weights(Ctx &c) {
   c.tc_weights_valid = true;
 }
 
+// x_pre: x_hat of these rows already featurized (on another stream) into that buffer
 void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords,
-                     bool keep) {
+                     bool keep, const SplitBuf *x_pre) {
   TcState &t = *c.tcs;
   tc_ensure_rows(c, M);
   ensure_tc_weights(c);
   const bool pairs = in_is_coords && c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
-  launch_featurize_split(c, in, gather, goff, M, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0]);
+  if (!x_pre) launch_featurize_split(c, in, gather, goff, M, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0]);
+  const SplitBuf &x0 = x_pre ? *x_pre : t.act[0];
   const int last = c.L - 1;
   const float *seg_last = c.params.p + c.off_w[last];
   for (int l = 0; l + 1 < c.L; ++l) {
     const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
     TcGemm g{};
-    g.a_hi = t.act[l].hi.p; g.a_lo = t.act[l].lo.p; g.lda = t.wp[l];
+    g.a_hi = l == 0 ? x0.hi.p : t.act[l].hi.p; g.a_lo = l == 0 ? x0.lo.p : t.act[l].lo.p; g.lda = t.wp[l];
     g.b_hi = t.wF[l].hi.p; g.b_lo = t.wF[l].lo.p; g.ldb = t.wp[l];
     g.M = (int)M; g.N = fout; g.K = fin;
     g.act = c.cfg.activation;
@@ -433,7 +435,49 @@ void compute_koopman(Ctx &c) {
   }
   const int64_t ch = chunk_rows(c, c.K);
   const int64_t nsp = ch / c.K;
-  for (int64_t n0 = 0; n0 < c.n_loc; n0 += nsp) {
+  const bool overlap = c.tc && !c.tcn && c.n_loc > nsp && !c.tc_no_overlap;
+  if (overlap) {
+    // Two streams: the featurizer (CUDA cores / LSU) of chunk i+1 runs next to the tensor-core GEMMs of chunk i.
+    // One featurizer block fits beside the resident GEMM CTA on every SM (28 KiB smem and ~27k registers are
+    // free), x_hat is double-buffered, events order producer and consumer.
+    TcState &t = *c.tcs;
+    const bool pairs = c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
+    if (!t.feat_stream) {
+      IK_CUDA(cudaStreamCreateWithFlags(&t.feat_stream, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) {
+        IK_CUDA(cudaEventCreateWithFlags(&t.feat_done[b], cudaEventDisableTiming));
+        IK_CUDA(cudaEventCreateWithFlags(&t.x_free[b], cudaEventDisableTiming));
+      }
+      IK_CUDA(cudaEventCreateWithFlags(&t.koop_start, cudaEventDisableTiming));
+    }
+    tc_ensure_rows(c, ch);
+    ensure_tc_weights(c);
+    t.x_alt.ensure(ch, t.wp[0]);
+    SplitBuf *bufs[2] = {&t.act[0], &t.x_alt};
+    IK_CUDA(cudaEventRecord(t.koop_start, c.stream));
+    IK_CUDA(cudaStreamWaitEvent(t.feat_stream, t.koop_start, 0));  // earlier work on the main stream owns the buffers
+    int i = 0;
+    for (int64_t n0 = 0; n0 < c.n_loc; n0 += nsp, ++i) {
+      const int64_t ns = std::min(nsp, c.n_loc - n0);
+      const int b = i & 1;
+      if (i >= 2) IK_CUDA(cudaStreamWaitEvent(t.feat_stream, t.x_free[b], 0));
+      if (c.ys_chunk_pts > 0) {
+        const int64_t last = std::min<int64_t>((n0 + ns - 1) / c.ys_chunk_pts, c.ys_chunks_pending - 1);
+        IK_CUDA(cudaStreamWaitEvent(t.feat_stream, c.ys_events[(size_t)last], 0));
+      }
+      std::swap(c.stream, t.feat_stream);
+      launch_featurize_split(c, c.ys + n0 * c.K * c.D, nullptr, 0, ns * c.K, pairs, c.ln, bufs[b]->hi.p, bufs[b]->lo.p,
+                             t.wp[0]);
+      std::swap(c.stream, t.feat_stream);
+      IK_CUDA(cudaEventRecord(t.feat_done[b], t.feat_stream));
+      IK_CUDA(cudaStreamWaitEvent(c.stream, t.feat_done[b], 0));
+      forward_rows_tc(c, nullptr, nullptr, 0, ns * c.K, true, false, bufs[b]);
+      IK_CUDA(cudaEventRecord(t.x_free[b], c.stream));
+      launch_kmean(c, c.act[c.L].p, c.has_weights ? c.kweights.p + n0 * c.K : nullptr, ns, (int)c.K, c.d,
+                   dst + n0 * c.d);
+    }
+  }
+  for (int64_t n0 = 0; n0 < c.n_loc && !overlap; n0 += nsp) {
     const int64_t ns = std::min(nsp, c.n_loc - n0);
     if (c.ys_chunk_pts > 0) {  // ys is still streaming in (isokann_set_data_async): wait for the covering chunk
       const int64_t last = std::min<int64_t>((n0 + ns - 1) / c.ys_chunk_pts, c.ys_chunks_pending - 1);
@@ -1042,6 +1086,7 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
     c->fused_train = cfg->gemm_mode == ISOKANN_GEMM_AUTO && !tc_eligible(*cfg, true) && narrow_train_eligible(*cfg);
     c->tiny = cfg->gemm_mode == ISOKANN_GEMM_AUTO && tiny_forward_eligible(*cfg);
     c->tc_no_pair = getenv("ISOKANN_TC_NO_PAIR") != nullptr;
+    c->tc_no_overlap = getenv("ISOKANN_OVERLAP") == nullptr;  // opt-in: measured +0.6 % under the 1 kW cap
     if (c->tc || c->tcn) {
       c->tcs = new TcState;
       c->tcs->act.resize(c->L);
@@ -1094,6 +1139,16 @@ int32_t isokann_destroy(isokann_ctx *c) {
     c->tcs->delta[1].release();
     c->tcs->dot_partial.release();
     c->tcs->dlast.release();
+    c->tcs->x_alt.release();
+    if (c->tcs->feat_stream) {
+      cudaStreamSynchronize(c->tcs->feat_stream);
+      cudaStreamDestroy(c->tcs->feat_stream);
+      for (int b = 0; b < 2; ++b) {
+        cudaEventDestroy(c->tcs->feat_done[b]);
+        cudaEventDestroy(c->tcs->x_free[b]);
+      }
+      cudaEventDestroy(c->tcs->koop_start);
+    }
     delete c->tcs;
   }
   c->pairs.release();

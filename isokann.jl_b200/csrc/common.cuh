@@ -185,6 +185,7 @@ struct Ctx {
   bool fused_train = false;   // narrow net + small minibatch: one fused fwd/loss/bwd kernel per step
   bool tcn = false;           // narrow net: inference forward = one tcgen05 GEMM with the MLP tail in its epilogue
   bool tc_weights_valid = false;
+  bool tc_no_overlap = false; // unless ISOKANN_OVERLAP=1: featurizer and GEMMs on one stream
   bool tc_no_pair = false;    // ISOKANN_TC_NO_PAIR=1: keep the 1-CTA GEMM (A/B comparison of the 2-CTA kernel)
   TcState *tcs = nullptr;
   DevBuf<int2> pairs;  // coordinate offsets (3a, 3b) per feature

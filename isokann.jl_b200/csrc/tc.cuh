@@ -67,6 +67,9 @@ struct TcState {
   std::vector<SplitBuf> wF;    // forward operand of layer l (l = 0..L-2): [w_{l+1} x wp_l]
   std::vector<SplitBuf> wD;    // dgrad operand of layer l   (l = 1..L-2): [w_l x wp_{l+1}]
   SplitBuf delta[2];           // row-major delta ping-pong
+  SplitBuf x_alt;              // second x_hat buffer: the featurizer of chunk i+1 overlaps the GEMMs of chunk i
+  cudaStream_t feat_stream = nullptr;
+  cudaEvent_t feat_done[2] = {nullptr, nullptr}, x_free[2] = {nullptr, nullptr}, koop_start = nullptr;
   SplitBuf dlast;              // split copy of the last layer's delta (B x d, padded to 64 columns)
   DevBuf<float> dot_partial;   // fused last layer: partial chi per 128-column slot
   std::vector<int> wp;         // padded widths
