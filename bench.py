@@ -311,23 +311,21 @@ def run_b200(args, pkg):
         ys_h.copy_(ys)
         torch.cuda.synchronize()
         xs_j, ys_j = xs_h.numpy().T, ys_h.numpy().T          # Julia-shaped (D, N), (D, K, n_loc) views
-        chi_host = np.empty((model.widths[-1], N), dtype=np.float32, order="F")
-        import ctypes as C
-        L = pkg.lib
+        nparams = eng.P
 
         def e2e_step(i):
-            # SimulationData upload + run!(iso, 1) + chis(iso) back on the host
+            # SimulationData upload + run!(iso, 1) + the loss and cpu(iso) (the updated model) back on the host
             eng.set_data_async(xs_j, ys_j, n_offset=off, n_local=n_loc)
             eng.iterate(w.target, 1, 1, B, perms[i % len(perms)], **opts)
-            eng._check(eng.lib.isokann_chis(eng.h, L.ptr(chi_host)))
+            eng.download_params()
         for i in range(2):
             e2e_step(i)
         ms_e = timed(e2e_step, nsteps)
         h2d = 4 * (xs.numel() + ys.numel()) + 8 * N
-        d2h = 8 + 4 * N * model.widths[-1]
+        d2h = 8 + 4 * nparams
         e2e = {"value": N * K * nsteps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / nsteps,
-               "call": "isokann_set_data_async (pinned host xs, ys; ys streamed behind the Koopman pass) + run!(iso,1) + chis(iso) to host"}
+               "call": "isokann_set_data_async (pinned host xs, ys streamed in behind the Koopman pass) + run!(iso,1) + loss and cpu(iso) parameters to host"}
         eng.set_data_dev(xs, ys, w.D, K, N, off, n_loc)
 
     if rank != 0:

@@ -139,11 +139,12 @@ int32_t isokann_set_data_f64(isokann_ctx *ctx, const double *xs, const double *y
  * [n_offset, n_offset+n_local) of this rank only. */
 int32_t isokann_set_data_sharded(isokann_ctx *ctx, const float *xs, const float *ys_local, int64_t D, int64_t K,
                                  int64_t N, int64_t n_offset, int64_t n_local);
-/* Asynchronous form of isokann_set_data_sharded: xs is copied before the call returns, ys_local is streamed
- * to the device on a second CUDA stream and the next Koopman pass (isokann_koopman / isokann_target /
- * isokann_iterate) consumes it chunk by chunk as it arrives, so the PCIe transfer overlaps the compute.
- * ys_local should be page-locked and must stay valid and unmodified until that pass (or
- * isokann_synchronize) has returned. */
+/* Asynchronous form of isokann_set_data_sharded: ys_local, then xs, are streamed to the device on a second
+ * CUDA stream.  The next Koopman pass (isokann_koopman / isokann_target / isokann_iterate) consumes ys chunk
+ * by chunk as it arrives and the first reader of xs (isokann_chis, training, an N-D target) waits for xs on
+ * the device, so the PCIe transfer overlaps the compute.  Both buffers should be page-locked and must stay
+ * valid and unmodified until isokann_synchronize (or a call that returns results computed from them, such
+ * as isokann_iterate) has returned. */
 int32_t isokann_set_data_async(isokann_ctx *ctx, const float *xs, const float *ys_local, int64_t D, int64_t K,
                                int64_t N, int64_t n_offset, int64_t n_local);
 /* addcoords!(iso, coords) / mergedata (src/simulation.jl:162-185, src/iso.jl:238): append n_new start points and

@@ -411,8 +411,16 @@ void allgather_rows(Ctx &c, const float *local, int64_t n_local, float *full) {
 }
 
 // chis(iso): model(features(xs)) on the resident start points -> c.chi_x (N x d)
+// xs uploaded by isokann_set_data_async is still in flight on the copy stream: order this stream behind it
+void wait_xs(Ctx &c) {
+  if (!c.xs_pending) return;
+  IK_CUDA(cudaStreamWaitEvent(c.stream, c.xs_event, 0));
+  c.xs_pending = false;
+}
+
 void compute_chis(Ctx &c) {
   IK_REQUIRE(c.xs != nullptr, ISOKANN_ERR_STATE, "no data: call isokann_set_data first");
+  wait_xs(c);
   c.chi_x.ensure((size_t)c.N * c.d);
   if (c.world == 1) {
     forward_to(c, c.xs, c.N, true, c.chi_x.p);
@@ -841,6 +849,7 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
 double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool partial) {
   IK_REQUIRE(c.xs != nullptr, ISOKANN_ERR_STATE, "no data: call isokann_set_data first");
   IK_REQUIRE(c.has_target, ISOKANN_ERR_STATE, "no target: call isokann_target / isokann_set_target first");
+  wait_xs(c);
   IK_REQUIRE(perm_host != nullptr, ISOKANN_BAD_ARGUMENT, "perm must not be NULL");
   IK_REQUIRE(minibatch >= 0, ISOKANN_BAD_ARGUMENT, "minibatch must be >= 0");
   const int64_t N = c.N;
@@ -889,9 +898,10 @@ void upload_rows(Ctx &c, const void *host, bool f64, int64_t count, float *dev) 
 
 void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_ptrs, int64_t D, int64_t K, int64_t N,
                    int64_t n_off, int64_t n_loc, bool async_ys = false) {
-  if (c.ys_chunk_pts > 0) {  // a previous asynchronous upload may still be running
+  if (c.ys_chunk_pts > 0 || c.xs_pending) {  // a previous asynchronous upload may still be running
     IK_CUDA(cudaStreamSynchronize(c.copy_stream));
     c.ys_chunk_pts = 0;
+    c.xs_pending = false;
   }
   IK_REQUIRE(xs != nullptr, ISOKANN_BAD_ARGUMENT, "xs must not be NULL");
   IK_REQUIRE(D == c.D, ISOKANN_BAD_ARGUMENT, "coordinate dimension does not match the featurizer/model");
@@ -908,7 +918,8 @@ void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_pt
     c.ys = (const float *)ys;
   } else {
     c.xs_own.ensure((size_t)N * D);
-    upload_rows(c, xs, f64, N * D, c.xs_own.p);
+    const bool async_all = async_ys && !f64 && ys && K > 0 && n_loc > 0;
+    if (!async_all) upload_rows(c, xs, f64, N * D, c.xs_own.p);
     c.xs = c.xs_own.p;
     c.ys = nullptr;
     if (ys && K > 0 && n_loc > 0) {
@@ -933,6 +944,11 @@ void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_pt
         }
         c.ys_chunk_pts = pts;
         c.ys_chunks_pending = nchunks;
+        // xs last: the Koopman pass reads ys only, so xs arrives while that pass is already running
+        if (!c.xs_event) IK_CUDA(cudaEventCreateWithFlags(&c.xs_event, cudaEventDisableTiming));
+        IK_CUDA(cudaMemcpyAsync(c.xs_own.p, xs, (size_t)N * D * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+        IK_CUDA(cudaEventRecord(c.xs_event, c.copy_stream));
+        c.xs_pending = true;
       } else {
         upload_rows(c, ys, f64, n_loc * K * D, c.ys_own.p);
       }
@@ -946,6 +962,14 @@ void build_pair_table(Ctx &c) {
   std::vector<int2> tab;
   auto upper = [&](const std::vector<int> &atoms) {  // column-major strict upper triangle (halfinds)
     const int n = (int)atoms.size();
+    c.tri_n = n;
+    if (g.featurizer == ISOKANN_FEAT_ATOMS && n > 0) {
+      std::vector<int> cmap(3 * (size_t)n);
+      for (int a = 0; a < n; ++a)
+        for (int k = 0; k < 3; ++k) cmap[3 * a + k] = 3 * atoms[a] + k;
+      c.tri_cmap.ensure(cmap.size());
+      IK_CUDA(cudaMemcpy(c.tri_cmap.p, cmap.data(), cmap.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     for (int j = 1; j < n; ++j)
       for (int i = 0; i < j; ++i) tab.push_back(make_int2(3 * atoms[i], 3 * atoms[j]));
   };
@@ -1086,6 +1110,7 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
     c->fused_train = cfg->gemm_mode == ISOKANN_GEMM_AUTO && !tc_eligible(*cfg, true) && narrow_train_eligible(*cfg);
     c->tiny = cfg->gemm_mode == ISOKANN_GEMM_AUTO && tiny_forward_eligible(*cfg);
     c->tc_no_pair = getenv("ISOKANN_TC_NO_PAIR") != nullptr;
+    { const char *e = getenv("ISOKANN_FEAT_REC"); c->feat_rec_off = e && e[0] == '0'; }
     c->tc_no_overlap = getenv("ISOKANN_OVERLAP") == nullptr;  // opt-in: measured +0.6 % under the 1 kW cap
     if (c->tc || c->tcn) {
       c->tcs = new TcState;
@@ -1166,6 +1191,7 @@ int32_t isokann_destroy(isokann_ctx *c) {
     cudaStreamDestroy(c->copy_stream);
   }
   for (auto e : c->ys_events) cudaEventDestroy(e);
+  if (c->xs_event) cudaEventDestroy(c->xs_event);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1241,9 +1267,10 @@ int32_t isokann_append_data(isokann_ctx *c, const float *xs_new, const float *ys
                "append needs library-owned data (isokann_set_data)");
     IK_REQUIRE(xs_new && D == c->D && n_new >= 0 && (c->K == 0 || (ys_new && K == c->K)), ISOKANN_BAD_ARGUMENT,
                "appended block must match D and K of the resident data");
-    if (c->ys_chunk_pts > 0) {
+    if (c->ys_chunk_pts > 0 || c->xs_pending) {
       IK_CUDA(cudaStreamSynchronize(c->copy_stream));
       c->ys_chunk_pts = 0;
+      c->xs_pending = false;
     }
     if (n_new == 0) return;
     const int64_t N0 = c->N, N1 = N0 + n_new;
@@ -1281,6 +1308,11 @@ int32_t isokann_keep_last(isokann_ctx *c, int64_t n_keep) {
                "keep_last needs library-owned data (isokann_set_data)");
     IK_REQUIRE(n_keep >= 1, ISOKANN_BAD_ARGUMENT, "n_keep must be positive");
     if (n_keep >= c->N) return;
+    if (c->ys_chunk_pts > 0 || c->xs_pending) {
+      IK_CUDA(cudaStreamSynchronize(c->copy_stream));
+      c->ys_chunk_pts = 0;
+      c->xs_pending = false;
+    }
     const int64_t drop = c->N - n_keep;
     auto shift = [&](DevBuf<float> &buf, int64_t per_point) {
       DevBuf<float> nb;
@@ -1606,6 +1638,7 @@ int32_t isokann_reset_stats(isokann_ctx *c) {
 int32_t isokann_synchronize(isokann_ctx *c) {
   return guarded(c, [&] {
     if (c->copy_stream) IK_CUDA(cudaStreamSynchronize(c->copy_stream));
+    c->xs_pending = false;
     sync_stream(*c);
   });
 }

@@ -1,5 +1,6 @@
 // Shared declarations of libisokann_b200: context, error handling, launch accounting.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -116,6 +117,10 @@ struct Ctx;
 void launch_featurize(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M, bool pairs,
                       bool do_ln, float *out, int64_t ldo);
 int launch_gemm(Ctx &c, const GemmP &p, bool a_kcontig, bool b_jcontig, int splits);  // returns splits used
+// lane = record featurizer (featurize_rec.cu): upper-triangle featurizers (all pairs / atom subset)
+bool featurize_rec_applicable(const Ctx &c, bool split, int64_t ld);
+void launch_featurize_rec(Ctx &c, const float *coords, const int64_t *gather, int64_t M, bool do_ln, float *out,
+                          __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld);
 void launch_featurize_backward(Ctx &c, const float *in, int64_t M, bool pairs, bool do_ln, const float *gxhat,
                                float *out);
 void launch_vjp_seed(Ctx &c, const float *chi, const float *cot, int64_t M, int d, int lastact, float *delta);
@@ -185,6 +190,9 @@ struct Ctx {
   bool fused_train = false;   // narrow net + small minibatch: one fused fwd/loss/bwd kernel per step
   bool tcn = false;           // narrow net: inference forward = one tcgen05 GEMM with the MLP tail in its epilogue
   bool tc_weights_valid = false;
+  int tri_n = 0;            // atoms of an upper-triangle featurizer (all pairs / atom subset), else 0
+  DevBuf<int> tri_cmap;     // atom subset: coordinate c of the selection -> coordinate of the record (else null)
+  bool feat_rec_off = false;  // ISOKANN_FEAT_REC=0: keep the lane = feature kernel (A/B comparison)
   bool tc_no_overlap = false; // unless ISOKANN_OVERLAP=1: featurizer and GEMMs on one stream
   bool tc_no_pair = false;    // ISOKANN_TC_NO_PAIR=1: keep the 1-CTA GEMM (A/B comparison of the 2-CTA kernel)
   TcState *tcs = nullptr;
@@ -204,6 +212,8 @@ struct Ctx {
   std::vector<cudaEvent_t> ys_events;
   int64_t ys_chunk_pts = 0;   // start points per upload chunk; 0 = no pending upload
   int64_t ys_chunks_pending = 0;
+  cudaEvent_t xs_event = nullptr;  // xs rides the copy stream behind ys (only the training side reads it)
+  bool xs_pending = false;
   DevBuf<float> chi_x, kchi, kchi_loc, gather_pad, target, w_loss;
   bool has_target = false;
 

@@ -347,6 +347,14 @@ static void launch_featurize_impl(Ctx &c, const float *coords, const int64_t *ga
   if (M <= 0) return;
   const int D = pairs ? c.D : c.F;  // identity featurizer: records are already features
   const int F = c.F;
+  if (pairs && featurize_rec_applicable(c, out_hi != nullptr, ldo)) {
+    c.timer.begin(KC_FEATURIZE, c.stream);
+    launch_featurize_rec(c, coords, gather ? gather + gather_off : nullptr, M, do_ln, out, out_hi, out_lo, ldo);
+    c.timer.end(c.stream);
+    IK_CUDA(cudaGetLastError());
+    c.count_launch(KC_FEATURIZE, 4.0 * (double)(D + F) * (double)M);
+    return;
+  }
   {
     // register-resident kernels: F (fp32 output) or the padded row (split output) must fit 32*NF, coordinate
     // offsets must fit the packed 16-bit table, 8 coordinate records must fit shared memory

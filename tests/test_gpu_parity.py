@@ -152,7 +152,15 @@ def test_nd_targets(pkg, oracle, d, kind, kw):
     xsf, ysf = oracle_features(oracle, w, xs, ys)
     ref = oracle.isotarget(kind, om, xsf, ysf, **kw)
     scale = np.abs(ref).max()
-    assert np.allclose(t, ref, rtol=2e-3, atol=2e-3 * scale), np.abs(t - ref).max() / scale
+    if kind == "pinv" and kw.get("eigenvecs", True):
+        # real Schur vectors of a random-init Kinv are rounding-sensitive (near-degenerate eigenvalues): a
+        # 1e-7 change of the features can reorder them, in LAPACK just as here -> compare the rows
+        # as a set
+        import itertools
+        err = min(np.abs(t[:, list(p)] - ref).max() for p in itertools.permutations(range(d)))
+        assert err < 2e-3 * scale, err / scale
+    else:
+        assert np.allclose(t, ref, rtol=2e-3, atol=2e-3 * scale), np.abs(t - ref).max() / scale
     if kind == "isa" and not kw.get("whitening"):
         # the d selected samples map to unit vectors (src/isotarget.jl:93,104)
         ks = oracle.expectation(om, ysf)
@@ -333,6 +341,20 @@ def test_async_upload_matches_blocking_upload(pkg, oracle):
     assert np.array_equal(k1[:, ::-1], k0)
     t = pkg.isotarget(iso)                              # target + training still work on the streamed data
     assert t.min() == 0.0 and t.max() == 1.0
+    xs2 = np.asfortranarray(xs[:, ::-1])                # xs rides the copy stream too: its first reader waits
+    iso.engine.set_data_async(xs2, ys2)
+    c1 = pkg.chis(iso)
+    iso.engine.set_data(xs2, ys2)
+    assert np.array_equal(c1, pkg.chis(iso))
+    perms = pkg.synthetic.make_perms(w, N, 1)
+    iso.engine.set_data_async(xs, ys)                   # straight into a full iteration
+    pkg.run_(iso, 1, perms=perms)
+    a = iso.engine.download_params()
+    iso.engine.upload_params(flat)
+    iso.engine.upload_opt_state(np.zeros_like(flat))
+    iso.engine.set_data(xs, ys)
+    pkg.run_(iso, 1, perms=perms)
+    assert np.array_equal(a, iso.engine.download_params())
 
 
 def test_tiny_net_forward_kernel(pkg, oracle):

@@ -106,6 +106,58 @@ def test_tc_two_cta_kernel(pkg, oracle):
     assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("name,widths,atoms,N", [("c1", [231, 256, 1], None, 77), ("c3", [595, 256, 256, 1], None, 1000),
+                                                ("c1", [91, 256, 1], [1, 2, 4, 5, 7, 9, 10, 12, 15, 17, 19, 20, 21, 22], 333)])
+def test_record_featurizer_matches_feature_featurizer(pkg, oracle, monkeypatch, name, widths, atoms, N):
+    # lane = record kernel (featurize_rec.cu, default for upper-triangle featurizers) against the lane = feature
+    # kernel (ISOKANN_FEAT_REC=0) and the oracle: ragged record blocks, atom subsets, gathered minibatches
+    w = wide(pkg, widths, name)
+    K = 3
+    xs, ys = pkg.synthetic.make_data(w, N, K)
+    om = oracle_model(oracle, w.widths, True, 5)
+    rng = np.random.default_rng(3)
+    om.ln_scale = rng.uniform(0.5, 1.5, widths[0]).astype(np.float32)
+    om.ln_bias = (0.1 * rng.normal(size=widths[0])).astype(np.float32)
+    flat = oracle.flatten_params(om)
+    feat = pkg.FeaturesAll() if atoms is None else pkg.FeaturesAtoms(atoms)
+
+    def build():
+        data = pkg.SimulationData(xs, ys, featurizer=feat)
+        model = pkg.Chain(list(w.widths), True).load_flat(flat)
+        return pkg.Iso(data, opt=pkg.AdamRegularized(), model=model, minibatch=max(32, N // 3), gemm="tc")
+    new = build()
+    monkeypatch.setenv("ISOKANN_FEAT_REC", "0")
+    old = build()
+    xf = oracle.flatpairdists(records(xs), atoms)
+    chi_ref = oracle.forward(om, xf)
+    c_new, c_old = records(pkg.chis(new)), records(pkg.chis(old))
+    assert np.allclose(c_new, chi_ref, rtol=TOL_CHI, atol=5e-5), np.abs(c_new - chi_ref).max()
+    assert np.abs(c_new - c_old).max() < 2e-5
+    assert np.abs(pkg.koopman(new) - pkg.koopman(old)).max() < 2e-5
+    perms = pkg.synthetic.make_perms(w, N, 2)
+    pkg.run_(new, 2, perms=perms)                       # gathered minibatches through the same kernel
+    pkg.run_(old, 2, perms=perms)
+    assert np.allclose(new.losses, old.losses, rtol=1e-4)
+    assert np.abs(pkg.chis(new) - pkg.chis(old)).max() < 2e-4
+
+
+def test_featurizer_gemm_overlap_is_bit_identical(pkg, oracle, monkeypatch):
+    # ISOKANN_OVERLAP=1: the featurizer of chunk i+1 runs on a second stream beside the GEMMs of chunk i
+    w = wide(pkg, [231, 256, 256, 1])
+    N, K = 3000, 4
+    xs, ys = pkg.synthetic.make_data(w, N, K)
+    flat = oracle.flatten_params(oracle_model(oracle, w.widths, True, 5))
+    plain = make_iso(pkg, w, xs, ys, flat, gemm="tc", chunk=1024)     # 12 chunks of 256 start points
+    k0 = pkg.koopman(plain)
+    monkeypatch.setenv("ISOKANN_OVERLAP", "1")
+    over = make_iso(pkg, w, xs, ys, flat, gemm="tc", chunk=1024)
+    for _ in range(3):
+        assert np.array_equal(pkg.koopman(over), k0)
+    pkg.run_(over, 2, perms=pkg.synthetic.make_perms(w, N, 2))
+    pkg.run_(plain, 2, perms=pkg.synthetic.make_perms(w, N, 2))
+    assert np.array_equal(pkg.chis(over), pkg.chis(plain))
+
+
 def test_full_size_c5_properties(pkg, oracle):
     """BASELINE config 5 at full size (N = 10^6, K = 16, pairnet [595, 2048, 2048, 1]) through size-independent
     properties; the data is generated on the device like bench.py does."""
