@@ -139,8 +139,9 @@ class Engine:
         self.N, self.K = N, K
 
     def set_data_async(self, xs, ys, n_offset: int = 0, n_local: Optional[int] = None):
-        """like set_data, but ys (float32, Fortran-ordered, ideally page-locked) is streamed in behind the
-        call and consumed chunk-wise by the next Koopman pass; the caller keeps ys alive until then"""
+        """like set_data, but ys and then xs (float32, Fortran-ordered, ideally page-locked) are streamed in
+        behind the call: the next Koopman pass consumes ys chunk-wise, the first reader of xs waits for it on
+        the device; the caller keeps both alive until results computed from them have come back"""
         xs = julia_f32(xs, 2)
         ys = julia_f32(ys, 3)
         D, N = xs.shape

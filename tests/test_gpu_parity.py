@@ -31,6 +31,26 @@ def test_flatpairdists_matches_oracle(pkg, oracle, name, M):
     assert (got >= 0).all()
 
 
+@pytest.mark.parametrize("A", [2, 3, 5, 9, 16, 33, 45, 54, 56, 70])
+def test_flatpairdists_atom_counts(pkg, oracle, A):
+    # every launch plan of the lane = record kernel (1/2/4/8 warps per block, 1..16 blocks per SM), the shared
+    # memory limit (A <= 54 fits, above that the lane = feature kernel takes over), ragged last record block,
+    # coincident atoms (distance exactly 0)
+    rng = np.random.default_rng(A)
+    M = 70
+    x = rng.normal(scale=0.5, size=(3 * A, M)).astype(np.float32)
+    x[3:6, 5] = x[0:3, 5]                                # atoms 1 and 2 of record 5 coincide
+    got = pkg.flatpairdists(np.asfortranarray(x))
+    ref = oracle.flatpairdists(records(x))
+    assert got.shape == (A * (A - 1) // 2, M)
+    assert np.allclose(records(got), ref, rtol=RTOL_DIST, atol=0)
+    assert got[0, 5] == 0.0
+    sub = list(range(A, 0, -2))                          # an atom subset in descending order (cmap path)
+    if len(sub) >= 2:
+        got = pkg.FeaturesAtoms(sub)(np.asfortranarray(x))
+        assert np.allclose(records(got), oracle.flatpairdists(records(x), sub), rtol=RTOL_DIST, atol=0)
+
+
 def test_flatpairdists_3d_input_and_float64(pkg, oracle):
     w = pkg.synthetic.WORKLOADS["c1"]
     xs, ys = pkg.synthetic.make_data(w, 33, 3, dtype=np.float64)

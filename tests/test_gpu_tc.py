@@ -141,6 +141,28 @@ def test_record_featurizer_matches_feature_featurizer(pkg, oracle, monkeypatch, 
     assert np.abs(pkg.chis(new) - pkg.chis(old)).max() < 2e-4
 
 
+@pytest.mark.parametrize("A", [12, 50])
+def test_record_featurizer_split_output_other_atom_counts(pkg, oracle, A):
+    # split (hi, lo) rows of the lane = record kernel for atom counts outside the BASELINE shapes: F = 66 fills
+    # exactly one 64-column octet plus a tail, F = 1225 needs 1280-column rows (one block per SM)
+    F = A * (A - 1) // 2
+    widths = [F, 256, 1]
+    rng = np.random.default_rng(A)
+    N, K = 45, 2
+    xs = np.asfortranarray(rng.normal(scale=0.5, size=(3 * A, N)).astype(np.float32))
+    ys = np.asfortranarray((xs[:, None, :] + 0.03 * rng.normal(size=(3 * A, K, N))).astype(np.float32))
+    om = oracle_model(oracle, widths, True, 5)
+    om.ln_scale = rng.uniform(0.5, 1.5, F).astype(np.float32)
+    om.ln_bias = (0.1 * rng.normal(size=F)).astype(np.float32)
+    data = pkg.SimulationData(xs, ys, featurizer=pkg.FeaturesAll())
+    model = pkg.Chain(widths, True).load_flat(oracle.flatten_params(om))
+    iso = pkg.Iso(data, opt=pkg.AdamRegularized(), model=model, minibatch=N, gemm="tc")
+    chi_ref = oracle.forward(om, oracle.flatpairdists(records(xs)))
+    assert np.allclose(records(pkg.chis(iso)), chi_ref, rtol=TOL_CHI, atol=5e-5)
+    k_ref = oracle.expectation(om, oracle.flatpairdists(records(ys)))
+    assert np.allclose(records(pkg.koopman(iso)), k_ref, rtol=TOL_CHI, atol=5e-5)
+
+
 def test_featurizer_gemm_overlap_is_bit_identical(pkg, oracle, monkeypatch):
     # ISOKANN_OVERLAP=1: the featurizer of chunk i+1 runs on a second stream beside the GEMMs of chunk i
     w = wide(pkg, [231, 256, 256, 1])
