@@ -35,15 +35,15 @@ __device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, f
 
 // Columns j0 .. j0+JT-1 of the strict upper triangle against all atoms i < j.  at = staged atoms + lane,
 // dt = parked-distance row of feature (0, j0) + lane.  Feature (i, j0+k) sits k*j0 + k(k-1)/2 + i rows after dt.
-template <int JT>
+template <int JT, int SC>  // SC: words between consecutive coordinates of one record in the staged block
 __device__ __forceinline__ void sweep_tile(const float *at, int j0, float &s, float &q, float *dt) {
   float cx[JT], cy[JT], cz[JT];
 #pragma unroll
   for (int k = 0; k < JT; ++k) {
-    const float *p = at + 3 * (j0 + k) * RP;
+    const float *p = at + 3 * (j0 + k) * SC;
     cx[k] = p[0];
-    cy[k] = p[RP];
-    cz[k] = p[2 * RP];
+    cy[k] = p[SC];
+    cz[k] = p[2 * SC];
   }
   float s2[JT], q2[JT];
 #pragma unroll
@@ -52,12 +52,12 @@ __device__ __forceinline__ void sweep_tile(const float *at, int j0, float &s, fl
   // staged block: atom j0 exists, and the row after the last atom is the start of the parked distances)
   const float *ap = at;
   float *dp = dt;
-  float ax = ap[0], ay = ap[RP], az = ap[2 * RP];
-  float bx = ap[3 * RP], by = ap[4 * RP], bz = ap[5 * RP];
+  float ax = ap[0], ay = ap[SC], az = ap[2 * SC];
+  float bx = ap[3 * SC], by = ap[4 * SC], bz = ap[5 * SC];
 #pragma unroll 4
   for (int i = 0; i < j0; ++i) {
-    ap += 3 * RP;
-    const float nx = ap[3 * RP], ny = ap[4 * RP], nz = ap[5 * RP];
+    ap += 3 * SC;
+    const float nx = ap[3 * SC], ny = ap[4 * SC], nz = ap[5 * SC];
 #pragma unroll
     for (int k = 0; k < JT; ++k) {
       float sq;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256, 2)
     featurize_blk_kernel(const float *__restrict__ coords, const int64_t *__restrict__ gather, int64_t M, int D, int A,
                          const int *__restrict__ cmap, int F, int do_ln, float eps2, float *__restrict__ out,
                          __nv_bfloat16 *__restrict__ out_hi, __nv_bfloat16 *__restrict__ out_lo, int64_t ldo) {
-  extern __shared__ float smem_f[];
+  extern __shared__ __align__(16) float smem_f[];
   const int W = blockDim.x >> 5;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = 3 * A;
@@ -115,8 +115,10 @@ __global__ void __launch_bounds__(256, 2)
   const float invF = 1.0f / (float)F;
   const int T = A >> 1;  // tiles of two columns: j0 = 1, 3, ...; the last one has a single column if A is even
   // Staging of one block of 32 records: 4-byte cp.async copies straight into the transposed layout (no registers,
-  // one wait).  Issuing the copies of block i+1 before pass 2 of block i was measured slower (the second
-  // resident block already covers the latency; the early copies only lengthen the store-bound pass 2).
+  // one wait).  Two alternatives were measured and dropped (profiles/r01_ncu_featurize_blk_v6.md): issuing the
+  // copies of block i+1 under pass 2 of block i (slower: they lengthen the store-bound pass 2, and the second
+  // resident block already covers the latency), and one cp.async.bulk per block into an untransposed layout
+  // (10 instead of 86 instructions per record, same time: the kernel is bound by MIO/LSU latency, not by issue).
   const uint32_t atoms_s = (uint32_t)__cvta_generic_to_shared(atoms);
   const int nfull = C >> 5, ctail = lane + (nfull << 5);
   auto issue = [&](int64_t blk_) {
@@ -161,8 +163,8 @@ __global__ void __launch_bounds__(256, 2)
           if (u < T) {
             const int j0 = 1 + 2 * (T - 1 - u);
             float *dt = dist + ((j0 * (j0 - 1)) >> 1) * RP + lane;
-            if (j0 + 1 < A) sweep_tile<2>(at, j0, s, q, dt);
-            else sweep_tile<1>(at, j0, s, q, dt);
+            if (j0 + 1 < A) sweep_tile<2, RP>(at, j0, s, q, dt);
+            else sweep_tile<1, RP>(at, j0, s, q, dt);
           }
         }
       }
@@ -202,22 +204,17 @@ __global__ void __launch_bounds__(256, 2)
         const int orec = rec < nvalid ? rec : nvalid - 1;
         const float *p = dist + (q8 << 3) * RP + rec;
         __nv_bfloat16 *oh = out_hi + (m0 + orec) * ldo + (q8 << 3), *ol = out_lo + (m0 + orec) * ldo + (q8 << 3);
-        // the raw distances of octet i+1 are loaded before octet i is converted and stored: the loads never wait for
-        // registers that a store still has to read, and their latency hides behind the conversion
-        float cur[8];
+        // Two register sets alternate: the raw distances of octet i+1 are loaded before octet i is converted and
+        // stored, so the loads never wait for registers that a 16-byte store still has to read, and their latency
+        // hides behind the conversion.
+        auto load8 = [&](float (&r)[8], const float *pp) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) cur[k] = p[k * RP];
-#pragma unroll 2
-        for (int oct = 0; oct < noct; ++oct) {
-          float nxt[8];
-          p += 64 * RP;
-          if (oct + 1 < noct) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) nxt[k] = p[k * RP];
-          }
+          for (int k = 0; k < 8; ++k) r[k] = pp[k * RP];
+        };
+        auto emit = [&](const float (&r)[8], int oct, __nv_bfloat16 *ph, __nv_bfloat16 *pl) {
           float v[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = fmaf(cur[k], ss.x, ss.y);
+          for (int k = 0; k < 8; ++k) v[k] = fmaf(r[k], ss.x, ss.y);
           if (oct >= full) {
             // column F carries the constant 1 of the augmented weight-gradient GEMM, the rest of the padded row is
             // 0 (the rows read past F belong to the padding of the parked distances and are discarded here)
@@ -230,12 +227,19 @@ __global__ void __launch_bounds__(256, 2)
           split2(v[2], v[3], h.y, l.y);
           split2(v[4], v[5], h.z, l.z);
           split2(v[6], v[7], h.w, l.w);
-          *reinterpret_cast<uint4 *>(oh) = h;
-          *reinterpret_cast<uint4 *>(ol) = l;
-          oh += 64;
-          ol += 64;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+          *reinterpret_cast<uint4 *>(ph) = h;
+          *reinterpret_cast<uint4 *>(pl) = l;
+        };
+        float ra[8], rb[8];
+        load8(ra, p);
+        for (int oct = 0; oct < noct; oct += 2) {
+          if (oct + 1 < noct) load8(rb, p + 64 * RP);
+          emit(ra, oct, oh, ol);
+          if (oct + 2 < noct) load8(ra, p + 128 * RP);
+          if (oct + 1 < noct) emit(rb, oct + 1, oh + 64, ol + 64);
+          p += 128 * RP;
+          oh += 128;
+          ol += 128;
         }
       }
     } else {
