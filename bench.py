@@ -321,8 +321,10 @@ def run_b200(args, pkg):
         for i in range(2):
             e2e_step(i)
         ms_e = timed(e2e_step, nsteps)
-        h2d = 4 * (xs.numel() + ys.numel()) + 8 * N
-        d2h = 8 + 4 * nparams
+        # whole job, all ranks together: every rank uploads its shard of ys, its own rows of xs (the other rows come
+        # from the peers over NVLink) and the permutation; every rank reads the loss and the parameters back
+        h2d = 4 * (xs.numel() + N * K * xs.shape[1]) + 8 * N * world
+        d2h = (8 + 4 * nparams) * world
         e2e = {"value": N * K * nsteps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / nsteps,
                "call": "isokann_set_data_async (pinned host xs, ys streamed in behind the Koopman pass) + run!(iso,1) + loss and cpu(iso) parameters to host"}

@@ -396,18 +396,19 @@ void forward_to(Ctx &c, const float *dev_in, int64_t M, bool in_is_coords, float
   }
 }
 
-void allgather_rows(Ctx &c, const float *local, int64_t n_local, float *full) {
+void allgather_rows(Ctx &c, const float *local, int64_t n_local, float *full, int width = 0) {
   // shards follow split_range(N); pad every shard to nmax rows for the fixed-size collective
+  const int64_t wd = width > 0 ? width : c.d;
   const int64_t nmax = (c.N + c.world - 1) / c.world;
-  c.gather_pad.ensure((size_t)(c.world + 1) * nmax * c.d);
-  float *send = c.gather_pad.p + (size_t)c.world * nmax * c.d;
-  IK_CUDA(cudaMemsetAsync(send, 0, (size_t)nmax * c.d * sizeof(float), c.stream));
-  IK_CUDA(cudaMemcpyAsync(send, local, (size_t)n_local * c.d * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  c.gather_pad.ensure((size_t)(c.world + 1) * nmax * wd);
+  float *send = c.gather_pad.p + (size_t)c.world * nmax * wd;
+  IK_CUDA(cudaMemsetAsync(send, 0, (size_t)nmax * wd * sizeof(float), c.stream));
+  IK_CUDA(cudaMemcpyAsync(send, local, (size_t)n_local * wd * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
   std::string err;
-  int rc = nccl_allgather_f32(c.nccl, c.comm, send, c.gather_pad.p, (size_t)nmax * c.d, c.stream, err);
+  int rc = nccl_allgather_f32(c.nccl, c.comm, send, c.gather_pad.p, (size_t)nmax * wd, c.stream, err);
   IK_REQUIRE(rc == ISOKANN_OK, ISOKANN_ERR_NCCL, err);
   c.stats.nccl_calls++;
-  launch_compact_gather(c, c.gather_pad.p, c.world, nmax, c.N, c.d, full);
+  launch_compact_gather(c, c.gather_pad.p, c.world, nmax, c.N, (int)wd, full);
 }
 
 // chis(iso): model(features(xs)) on the resident start points -> c.chi_x (N x d)
@@ -416,6 +417,27 @@ void wait_xs(Ctx &c) {
   if (!c.xs_pending) return;
   IK_CUDA(cudaStreamWaitEvent(c.stream, c.xs_event, 0));
   c.xs_pending = false;
+}
+
+// After a multi-rank isokann_set_data_async every rank holds only its own rows of xs (they came over PCIe); the
+// training side gathers by the global permutation, so the other ranks' rows are fetched over NVLink here: in place
+// when the shards are equal, through the padded buffer otherwise.
+void gather_xs(Ctx &c) {
+  wait_xs(c);
+  if (!c.xs_gather_pending) return;
+  c.xs_gather_pending = false;
+  float *xs = c.xs_own.p;
+  if (c.N % c.world == 0) {
+    std::string err;
+    int rc = nccl_allgather_f32(c.nccl, c.comm, xs + c.n_off * c.D, xs, (size_t)c.n_loc * c.D, c.stream, err);
+    IK_REQUIRE(rc == ISOKANN_OK, ISOKANN_ERR_NCCL, err);
+    c.stats.nccl_calls++;
+  } else {
+    c.xs_stage.ensure((size_t)std::max<int64_t>(1, c.n_loc) * c.D);
+    IK_CUDA(cudaMemcpyAsync(c.xs_stage.p, xs + c.n_off * c.D, (size_t)c.n_loc * c.D * sizeof(float),
+                            cudaMemcpyDeviceToDevice, c.stream));
+    allgather_rows(c, c.xs_stage.p, c.n_loc, xs, (int)c.D);
+  }
 }
 
 void compute_chis(Ctx &c) {
@@ -849,7 +871,7 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
 double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool partial) {
   IK_REQUIRE(c.xs != nullptr, ISOKANN_ERR_STATE, "no data: call isokann_set_data first");
   IK_REQUIRE(c.has_target, ISOKANN_ERR_STATE, "no target: call isokann_target / isokann_set_target first");
-  wait_xs(c);
+  gather_xs(c);
   IK_REQUIRE(perm_host != nullptr, ISOKANN_BAD_ARGUMENT, "perm must not be NULL");
   IK_REQUIRE(minibatch >= 0, ISOKANN_BAD_ARGUMENT, "minibatch must be >= 0");
   const int64_t N = c.N;
@@ -903,6 +925,7 @@ void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_pt
     c.ys_chunk_pts = 0;
     c.xs_pending = false;
   }
+  c.xs_gather_pending = false;
   IK_REQUIRE(xs != nullptr, ISOKANN_BAD_ARGUMENT, "xs must not be NULL");
   IK_REQUIRE(D == c.D, ISOKANN_BAD_ARGUMENT, "coordinate dimension does not match the featurizer/model");
   IK_REQUIRE(N > 0 && K >= 0, ISOKANN_BAD_ARGUMENT, "N must be positive");
@@ -946,7 +969,14 @@ void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_pt
         c.ys_chunks_pending = nchunks;
         // xs last: the Koopman pass reads ys only, so xs arrives while that pass is already running
         if (!c.xs_event) IK_CUDA(cudaEventCreateWithFlags(&c.xs_event, cudaEventDisableTiming));
-        IK_CUDA(cudaMemcpyAsync(c.xs_own.p, xs, (size_t)N * D * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+        if (c.world > 1) {  // only this rank's rows cross PCIe; gather_xs() fetches the rest from the peers
+          IK_CUDA(cudaMemcpyAsync(c.xs_own.p + n_off * D, (const float *)xs + n_off * D,
+                                  (size_t)n_loc * D * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+          c.xs_gather_pending = true;
+        } else {
+          IK_CUDA(cudaMemcpyAsync(c.xs_own.p, xs, (size_t)N * D * sizeof(float), cudaMemcpyHostToDevice,
+                                  c.copy_stream));
+        }
         IK_CUDA(cudaEventRecord(c.xs_event, c.copy_stream));
         c.xs_pending = true;
       } else {
@@ -1154,7 +1184,8 @@ int32_t isokann_destroy(isokann_ctx *c) {
   for (auto &a : c->act) a.release();
   DevBuf<float> *fb[] = {&c->params, &c->grads, &c->opt_m, &c->opt_v, &c->folded1, &c->gfold, &c->xs_own, &c->ys_own,
                          &c->kweights, &c->chi_x, &c->kchi, &c->kchi_loc, &c->gather_pad, &c->target, &c->w_loss,
-                         &c->delta_a, &c->delta_b, &c->splitk, &c->staging_in, &c->staging_out, &c->red_f};
+                         &c->delta_a, &c->delta_b, &c->splitk, &c->staging_in, &c->staging_out, &c->red_f,
+                         &c->xs_stage};
   for (auto *b : fb) b->release();
   if (c->tcs) {
     for (auto &b : c->tcs->act) b.release();
@@ -1176,6 +1207,7 @@ int32_t isokann_destroy(isokann_ctx *c) {
     }
     delete c->tcs;
   }
+  c->tri_cmap.release();
   c->pairs.release();
   c->adj_off.release();
   c->adj.release();

@@ -214,6 +214,8 @@ struct Ctx {
   int64_t ys_chunks_pending = 0;
   cudaEvent_t xs_event = nullptr;  // xs rides the copy stream behind ys (only the training side reads it)
   bool xs_pending = false;
+  DevBuf<float> xs_stage;          // send buffer of the padded xs all-gather (unequal shards)
+  bool xs_gather_pending = false;  // multi-rank async upload: only this rank's rows of xs came from the host
   DevBuf<float> chi_x, kchi, kchi_loc, gather_pad, target, w_loss;
   bool has_target = false;
 

@@ -58,6 +58,16 @@ def main():
         st = multi.engine.stats()
         if not ok or st["nccl_calls"] == 0:
             failures.append((name, target, multi.losses, single.losses, float(np.abs(chi_m - chi_s).max())))
+        # asynchronous upload: every rank sends only its own rows of xs over PCIe and fetches the rest from its peers
+        # (in place for equal shards, padded otherwise); must reproduce the blocking upload bit for bit
+        uid2 = pkg.parallel.broadcast_unique_id(rank)
+        again = make((world, rank, uid2))
+        off, n = pkg.parallel.shard_range(N, world, rank)
+        again.engine.set_data_async(xs, np.asfortranarray(ys[:, :, off:off + n]), n_offset=off, n_local=n)
+        pkg.run_(again, 3, perms=perms)
+        if not (np.array_equal(again.losses, multi.losses)
+                and np.array_equal(again.engine.download_params(), flat_m) and np.array_equal(pkg.chis(again), chi_m)):
+            failures.append((name, "async upload differs", again.losses, multi.losses))
         # every rank must hold identical parameters
         t = torch.from_numpy(flat_m.copy()).cuda()
         ref = t.clone()
