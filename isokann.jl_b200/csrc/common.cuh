@@ -213,6 +213,15 @@ struct Ctx {
   int64_t ys_chunk_pts = 0;   // start points per upload chunk; 0 = no pending upload
   int64_t ys_chunks_pending = 0;
   cudaEvent_t xs_event = nullptr;  // xs rides the copy stream behind ys (only the training side reads it)
+  // cudaFuncSetAttribute is per device: remembered per context, not per process (one process may hold contexts
+  // on several devices)
+  enum { ATTR_FEAT_BWD = 0, ATTR_FEAT_LN, ATTR_FEAT_BLK0, ATTR_NARROW = 6, ATTR_TC1, ATTR_TC2 };
+  uint32_t func_attr_done = 0;
+  bool attr_needed(int bit) {
+    if (func_attr_done >> bit & 1u) return false;
+    func_attr_done |= 1u << bit;
+    return true;
+  }
   bool xs_pending = false;
   DevBuf<float> xs_stage;          // send buffer of the padded xs all-gather (unequal shards)
   bool xs_gather_pending = false;  // multi-rank async upload: only this rank's rows of xs came from the host

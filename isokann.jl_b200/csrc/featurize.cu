@@ -323,11 +323,8 @@ void launch_featurize_backward(Ctx &c, const float *in, int64_t M, bool pairs, b
     smem = (size_t)warps * (Dp + 2 * Fp) * sizeof(float);
   }
   IK_REQUIRE(smem <= 200 * 1024, ISOKANN_BAD_ARGUMENT, "feature dimension too large for the featurizer pullback");
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (c.attr_needed(Ctx::ATTR_FEAT_BWD))
     IK_CUDA(cudaFuncSetAttribute(featurize_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
   int64_t want = (M + warps - 1) / warps;
   int grid = (int)std::min<int64_t>(want, (int64_t)c.num_sms * 8);
   const float eps = c.cfg.ln_eps;
@@ -388,11 +385,8 @@ static void launch_featurize_impl(Ctx &c, const float *coords, const int64_t *ga
     smem = (size_t)warps * (Dp + Fp) * sizeof(float);
   }
   IK_REQUIRE(smem <= 200 * 1024, ISOKANN_BAD_ARGUMENT, "feature dimension too large for the featurizer kernel");
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (c.attr_needed(Ctx::ATTR_FEAT_LN))
     IK_CUDA(cudaFuncSetAttribute(featurize_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
   int64_t want = (M + warps - 1) / warps;
   int64_t cap = (int64_t)c.num_sms * 8;
   int grid = (int)(want < cap ? want : cap);

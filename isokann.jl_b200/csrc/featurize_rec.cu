@@ -299,12 +299,9 @@ void launch_featurize_rec(Ctx &c, const float *coords, const int64_t *gather, in
   const int64_t nblk = (M + 31) / 32;
   const int grid = (int)std::min<int64_t>(nblk, (int64_t)c.num_sms * p.blocks_per_sm);
   const float eps = c.cfg.ln_eps;
-  static bool attr_set[4] = {false, false, false, false};  // per kernel instantiation
-  auto go = [&](auto kernel, int id) {
-    if (!attr_set[id]) {
+  auto go = [&](auto kernel, int id) {  // id: one attribute flag per kernel instantiation
+    if (c.attr_needed(Ctx::ATTR_FEAT_BLK0 + id))
       IK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set[id] = true;
-    }
     kernel<<<grid, p.warps * 32, p.smem, c.stream>>>(coords, gather, M, c.D, A, c.tri_cmap.p, A * (A - 1) / 2,
                                                      do_ln ? 1 : 0, eps * eps, out, out_hi, out_lo, ld);
   };

@@ -418,11 +418,8 @@ void launch_narrow_train(Ctx &c, const float *xhat, int64_t Bloc, const int64_t 
   c.red_d.ensure((size_t)std::max(nparts, 1024));
   p.part = c.splitk.p; p.part_stride = stride; p.part_loss = c.red_d.p;
   const size_t smem = ((size_t)F * R + (2 + KQ - 1) * R * H1P + 2 * ISOKANN_MAX_LAYERS * R * TW) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  if (c.attr_needed(Ctx::ATTR_NARROW))
     IK_CUDA(cudaFuncSetAttribute(narrow_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
   c.timer.begin(KC_GEMM, c.stream);
   narrow_fwd_bwd_kernel<<<nparts, NT, smem, c.stream>>>(p);
   c.timer.end(c.stream);

@@ -778,14 +778,12 @@ void make_map_mn(CUtensorMap *m, const void *ptr, int64_t mn_extent, int64_t k_e
 
 int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
-  static bool attr = false;
-  if (!attr) {
+  if (c.attr_needed(Ctx::ATTR_TC1)) {
     IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_BIAS_ACT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_MULDACT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_BIAS_ACT_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     IK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TC_EPI_TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr = true;
   }
   alignas(64) CUtensorMap mah, mal, mbh, mbl;
   if (g.mn_major) {
@@ -838,12 +836,10 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   const bool pair = !g.mn_major && g.epi != TC_EPI_F32 && g.epi != TC_EPI_TAIL && g.N > BN / 2 &&
                     m_tiles2 * p.n_tiles >= c.num_sms / 2 && !c.tc_no_pair;
   if (pair) {
-    static bool attr2 = false;
-    if (!attr2) {
+    if (c.attr_needed(Ctx::ATTR_TC2)) {
       IK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_EPI_BIAS_ACT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
       IK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_EPI_MULDACT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
       IK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_EPI_BIAS_ACT_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-      attr2 = true;
     }
     make_map(&mbh, g.b_hi, g.N, g.K, g.ldb, BN / 2);  // each CTA of the pair loads half of the B tile
     make_map(&mbl, g.b_lo, g.N, g.K, g.ldb, BN / 2);
