@@ -213,3 +213,70 @@ def test_chi_vjp_matches_finite_differences(oracle):
         assert abs(fd - g[i, k]) < 1e-6 * max(1.0, abs(fd)), (fd, g[i, k])
     # rigid translation does not change chi: the gradient sums to zero over atoms
     assert np.abs(g.reshape(3, 6, 3).sum(axis=1)).max() < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# independent implementations (torch autograd / torch.optim): not the reference, but a second,
+# widely used implementation of the same published arithmetic -- a tighter pin than finite differences
+# ---------------------------------------------------------------------------------------------
+def _torch_model(oracle, om, x64):
+    """the oracle Model evaluated with torch ops in float64; returns (chi, leaf parameter tensors in flat order)"""
+    import torch
+    t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), requires_grad=True)
+    leaves = []
+    h = torch.tensor(x64)
+    if om.layernorm:
+        g, b = t(om.ln_scale), t(om.ln_bias)
+        leaves += [g, b]
+        h = torch.nn.functional.layer_norm(h, (h.shape[1],), eps=om.ln_eps ** 2) * g + b   # Flux: sqrt(var + eps^2)
+    for i, (W, bb) in enumerate(zip(om.W, om.b)):
+        Wt, bt = t(W), t(bb)
+        leaves += [Wt, bt]
+        h = h @ Wt + bt
+        if i < om.nlayers - 1:
+            h = torch.sigmoid(h)
+    return h, leaves
+
+
+@pytest.mark.parametrize("d", [1, 3])
+def test_gradient_matches_torch_autograd(oracle, d):
+    import torch
+    rng = np.random.default_rng(0)
+    om = oracle.densenet([12, 7, 5, d], layernorm=True, rng=rng)
+    om.ln_scale = rng.uniform(0.5, 1.5, 12).astype(np.float32)
+    om.ln_bias = (0.1 * rng.normal(size=12)).astype(np.float32)
+    om.b = [(0.1 * rng.normal(size=b.shape)).astype(np.float32) for b in om.b]
+    x = rng.normal(size=(9, 12)).astype(np.float32)
+    y = rng.uniform(size=(9, d)).astype(np.float32)
+    w = None if d == 1 else rng.uniform(0.5, 2.0, d).astype(np.float32)
+    l, g = oracle.batch_loss_and_grad(om, x, y, w)
+    chi, leaves = _torch_model(oracle, om, x.astype(np.float64))
+    wt = torch.ones(d, dtype=torch.float64) if w is None else torch.tensor(w.astype(np.float64))
+    lt = (((chi - torch.tensor(y.astype(np.float64))) * wt) ** 2).sum()
+    (lt / x.shape[0]).backward()
+    # flat order: [gamma, beta,] W1 (in Julia's memory order = the oracle's (in, out) row-major), b1, ...
+    gt = np.concatenate([p.grad.numpy().ravel() for p in leaves])
+    assert np.isclose(l, lt.item(), rtol=1e-5)
+    assert np.allclose(g, gt, rtol=2e-4, atol=2e-6), np.abs(g - gt).max()
+
+
+@pytest.mark.parametrize("kind", ["adam", "nesterov"])
+def test_optimiser_matches_torch_optim(oracle, kind):
+    # Optimisers.jl OptimiserChain(WeightDecay(lam), Adam/Nesterov) == torch Adam / SGD(nesterov) with L2 weight decay
+    import torch
+    rng = np.random.default_rng(1)
+    theta = rng.normal(size=50).astype(np.float32)
+    cfg = oracle.OptConfig(kind=kind, eta=1e-2, lam=1e-3)
+    st = oracle.opt_init(cfg, theta.size)
+    p = torch.tensor(theta.astype(np.float64), requires_grad=True)
+    if kind == "adam":
+        opt = torch.optim.Adam([p], lr=cfg.eta, betas=(cfg.beta1, cfg.beta2), eps=cfg.eps, weight_decay=cfg.lam)
+    else:
+        opt = torch.optim.SGD([p], lr=cfg.eta, momentum=cfg.rho, nesterov=True, weight_decay=cfg.lam)
+    th = theta.copy()
+    for step in range(25):
+        g = rng.normal(size=50).astype(np.float32)
+        th = oracle.opt_update(cfg, st, th, g)
+        p.grad = torch.tensor(g.astype(np.float64))
+        opt.step()
+        assert np.allclose(th, p.detach().numpy(), rtol=2e-4, atol=2e-6), (step, np.abs(th - p.detach().numpy()).max())
