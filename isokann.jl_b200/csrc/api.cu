@@ -267,6 +267,7 @@ void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t gof
     g.out_hi = t.act[l + 1].hi.p; g.out_lo = t.act[l + 1].lo.p; g.ldo = t.wp[l + 1];
     launch_tc_gemm(c, g);
   }
+  if (c.head_fused_now) return;  // training step: launch_thin_head does the last layer together with its backward
   launch_thin_forward(c, t.act[last].hi.p, t.act[last].lo.p, M, c.cfg.widths[last], t.wp[last], seg_last, c.d,
                       c.cfg.last_activation, c.act[c.L].p);
 }
@@ -297,19 +298,25 @@ void forward_rows_tcn(Ctx &c, const float *in, const int64_t *gather, int64_t go
 
 // backward + gradient assembly of one minibatch slice on the tensor-core path; forward_rows_tc and
 // launch_loss_delta (delta of the last layer in c.delta_a, B x d fp32) have already run
-void backward_tc(Ctx &c, int64_t Bloc) {
+void tc_ensure_delta(Ctx &c, int64_t Bloc) {
   TcState &t = *c.tcs;
-  const int L = c.L, d = c.d;
   int wpmax = 0;
-  for (int l = 0; l < L; ++l) wpmax = std::max(wpmax, t.wp[l]);
+  for (int l = 0; l < c.L; ++l) wpmax = std::max(wpmax, t.wp[l]);
   t.delta[0].ensure(Bloc, wpmax);
   t.delta[1].ensure(Bloc, wpmax);
+  t.dlast.ensure(Bloc, 64);
+}
+
+// head_done: launch_thin_head already produced delta_L (split, t.dlast) and delta_{L-1} (t.delta[0])
+void backward_tc(Ctx &c, int64_t Bloc, bool head_done) {
+  TcState &t = *c.tcs;
+  const int L = c.L, d = c.d;
+  tc_ensure_delta(c, Bloc);
   int cur = 0;
   {  // last (thin) layer
     const int l = L - 1, fin = c.cfg.widths[l];
     // thin weight gradient [(fin+1) x d] = [z, 1]^T * delta_L on the same MN-major GEMM (N padded by TMA zero fill)
-    t.dlast.ensure(Bloc, 64);
-    launch_f32_to_split(c, c.delta_a.p, Bloc, d, t.dlast.hi.p, t.dlast.lo.p, 64);
+    if (!head_done) launch_f32_to_split(c, c.delta_a.p, Bloc, d, t.dlast.hi.p, t.dlast.lo.p, 64);
     TcGemm w{};
     w.mn_major = 1;
     w.a_hi = t.act[l].hi.p; w.a_lo = t.act[l].lo.p; w.lda = t.wp[l];
@@ -330,8 +337,9 @@ void backward_tc(Ctx &c, int64_t Bloc) {
       w.splits = 1;
       launch_tc_gemm(c, w);
     }
-    launch_thin_dgrad(c, c.delta_a.p, Bloc, d, c.params.p + c.off_w[l], fin, t.act[l].hi.p, t.act[l].lo.p, t.wp[l],
-                      c.cfg.activation, t.delta[cur].hi.p, t.delta[cur].lo.p, t.wp[l]);
+    if (!head_done)
+      launch_thin_dgrad(c, c.delta_a.p, Bloc, d, c.params.p + c.off_w[l], fin, t.act[l].hi.p, t.act[l].lo.p, t.wp[l],
+                        c.cfg.activation, t.delta[cur].hi.p, t.delta[cur].lo.p, t.wp[l]);
   }
   for (int l = L - 2; l >= 0; --l) {
     const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
@@ -804,13 +812,27 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
                        c.cfg.widths[1], c.grads.p + c.off_gamma, c.grads.p + c.off_beta, c.grads.p + c.off_w[0],
                        c.grads.p + c.off_b[0]);
   } else {
+    const bool head = c.tc && !c.tc_no_head && thin_head_eligible(c);
+    c.head_fused_now = head;
     forward_rows(c, c.xs, c.perm_dev.p, s0, Bloc, true, true);
+    c.head_fused_now = false;
     c.delta_a.ensure((size_t)Bloc * c.maxw);
     c.delta_b.ensure((size_t)Bloc * c.maxw);
     float *cur = c.delta_a.p, *other = c.delta_b.p;
-    launch_loss_delta(c, c.act[L].p, c.target.p, c.perm_dev.p, s0, c.w_loss.p, Bloc, d, (double)len,
-                      c.cfg.last_activation, cur, c.red_d.p, c.ticket.p, c.grads.p + c.P);
-    if (c.tc) backward_tc(c, Bloc);
+    if (head) {
+      TcState &t = *c.tcs;
+      const int last = L - 1;
+      tc_ensure_delta(c, Bloc);
+      c.red_d.ensure(1024);
+      launch_thin_head(c, t.act[last].hi.p, t.act[last].lo.p, Bloc, c.cfg.widths[last], t.wp[last],
+                       c.params.p + c.off_w[last], c.target.p, c.perm_dev.p + s0, c.w_loss.p, (double)len, c.act[L].p,
+                       cur, t.dlast.hi.p, t.dlast.lo.p, 64, t.delta[0].hi.p, t.delta[0].lo.p, t.wp[last], c.red_d.p,
+                       c.ticket.p, c.grads.p + c.P);
+    } else {
+      launch_loss_delta(c, c.act[L].p, c.target.p, c.perm_dev.p, s0, c.w_loss.p, Bloc, d, (double)len,
+                        c.cfg.last_activation, cur, c.red_d.p, c.ticket.p, c.grads.p + c.P);
+    }
+    if (c.tc) backward_tc(c, Bloc, head);
     for (int l = L - 1; l >= 0 && !c.tc; --l) {
       const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
       // weight + bias gradient: [(fin+1) x fout] = [act[l], 1]^T * delta
@@ -1140,6 +1162,7 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
     c->fused_train = cfg->gemm_mode == ISOKANN_GEMM_AUTO && !tc_eligible(*cfg, true) && narrow_train_eligible(*cfg);
     c->tiny = cfg->gemm_mode == ISOKANN_GEMM_AUTO && tiny_forward_eligible(*cfg);
     c->tc_no_pair = getenv("ISOKANN_TC_NO_PAIR") != nullptr;
+    c->tc_no_head = getenv("ISOKANN_TC_NO_HEAD") != nullptr;
     { const char *e = getenv("ISOKANN_FEAT_REC"); c->feat_rec_off = e && e[0] == '0'; }
     c->tc_no_overlap = getenv("ISOKANN_OVERLAP") == nullptr;  // opt-in: measured +0.6 % under the 1 kW cap
     if (c->tc || c->tcn) {

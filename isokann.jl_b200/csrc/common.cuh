@@ -194,6 +194,8 @@ struct Ctx {
   DevBuf<int> tri_cmap;     // atom subset: coordinate c of the selection -> coordinate of the record (else null)
   bool feat_rec_off = false;  // ISOKANN_FEAT_REC=0: keep the lane = feature kernel (A/B comparison)
   bool tc_no_overlap = false; // unless ISOKANN_OVERLAP=1: featurizer and GEMMs on one stream
+  bool tc_no_head = false;     // ISOKANN_TC_NO_HEAD=1: separate thin_forward / loss_delta / thin_dgrad kernels (A/B)
+  bool head_fused_now = false; // set around the forward pass of a training step whose thin head is fused
   bool tc_no_pair = false;    // ISOKANN_TC_NO_PAIR=1: keep the 1-CTA GEMM (A/B comparison of the 2-CTA kernel)
   TcState *tcs = nullptr;
   DevBuf<int2> pairs;  // coordinate offsets (3a, 3b) per feature

@@ -92,6 +92,12 @@ void launch_prep_weights(Ctx &c, const float *seg, int fin, int fout, __nv_bfloa
 void launch_thin_forward(Ctx &c, const __nv_bfloat16 *z_hi, const __nv_bfloat16 *z_lo, int64_t M, int fin, int64_t ldz,
                          const float *seg, int d, int act, float *chi);
 // delta_prev[m,k] = (sum_a delta[m,a] W[k,a]) * act'(z[m,k]) written split (row-major)
+bool thin_head_eligible(const Ctx &c);
+void launch_thin_head(Ctx &c, const __nv_bfloat16 *z_hi, const __nv_bfloat16 *z_lo, int64_t M, int fin, int64_t ldz,
+                      const float *seg, const float *target, const int64_t *idx, const float *wl, double Bglobal,
+                      float *chi, float *delta, __nv_bfloat16 *dl_hi, __nv_bfloat16 *dl_lo, int ld_dl,
+                      __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ldo, double *partials,
+                      unsigned int *ticket, float *packed_tail);
 void launch_thin_dgrad(Ctx &c, const float *delta, int64_t M, int d, const float *seg, int fin,
                        const __nv_bfloat16 *z_hi, const __nv_bfloat16 *z_lo, int64_t ldz, int act,
                        __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ldo);

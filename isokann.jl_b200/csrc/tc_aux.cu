@@ -191,7 +191,156 @@ __global__ void dot_finish_kernel(const float *__restrict__ partial, int64_t M, 
   }
 }
 
+// ---- thin head of a training step: last Dense layer + loss + both of its backward products, one warp per row ----
+// Replaces thin_forward -> loss_delta -> f32_to_split -> thin_dgrad (4 launches, z read twice) on the training path:
+//   chi = lastact(z W_L + b_L);  l += sum(((chi - y) .* w)^2)  (Float64 promotion for d == 1, src/iso.jl:183-185)
+//   delta_L = d(l/B)/d(pre-activation)           -> fp32 (B x d) and split bf16 (B operand of the thin weight gradient)
+//   delta_{L-1} = (delta_L W_L^T) .* act'(z)      -> split bf16 rows (operand of the next two GEMMs)
+// The row stays in registers between the dot product and the backward product.  The loss is reduced in a fixed
+// order (lane 0 of each warp over its rows, warps in order, last block over the block partials) and packed as
+// (hi, lo) floats behind the gradient vector exactly like loss_delta_kernel does.
+template <int NCH, int DT>  // NCH 16-byte chunks per lane (rows of up to 256 * NCH columns); DT = d at compile time
+__global__ void __launch_bounds__(256, 3)
+    thin_head_kernel(const __nv_bfloat16 *__restrict__ z_hi, const __nv_bfloat16 *__restrict__ z_lo, int64_t M, int fin,
+                     int64_t ldz, const float *__restrict__ seg, int d, int act, int lastact,
+                     const float *__restrict__ target, const int64_t *__restrict__ idx, const float *__restrict__ wl,
+                     double Bglobal, float *__restrict__ chi, float *__restrict__ delta,
+                     __nv_bfloat16 *__restrict__ dl_hi, __nv_bfloat16 *__restrict__ dl_lo, int ld_dl,
+                     __nv_bfloat16 *__restrict__ out_hi, __nv_bfloat16 *__restrict__ out_lo, int64_t ldo,
+                     double *__restrict__ partials, unsigned int *__restrict__ ticket, float *__restrict__ packed_tail) {
+  __shared__ double sh[8];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float invB = (float)(1.0 / Bglobal);
+  double lsum = 0.0;
+  for (int64_t m = wid; m < M; m += nw) {
+    const uint4 *ph = reinterpret_cast<const uint4 *>(z_hi + m * ldz);
+    const uint4 *pl = reinterpret_cast<const uint4 *>(z_lo + m * ldz);
+    // ---- chi = lastact(z W + b): the row is streamed once here and once more (from L1) for the backward product
+    float acc[DT];
+#pragma unroll
+    for (int a = 0; a < DT; ++a) acc[a] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int k8 = lane + 32 * j;
+      if (k8 * 8 < fin) {
+        const uint4 h = __ldg(ph + k8), l = __ldg(pl + k8);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = k8 * 8 + 2 * e;
+          const float z0 = bflo(hw[e]) + bflo(lw[e]);
+          const float z1 = bfhi(hw[e]) + bfhi(lw[e]);
+#pragma unroll
+          for (int a = 0; a < DT; ++a) {
+            if (k < fin) acc[a] = fmaf(z0, __ldg(seg + k * DT + a), acc[a]);
+            if (k + 1 < fin) acc[a] = fmaf(z1, __ldg(seg + (k + 1) * DT + a), acc[a]);
+          }
+        }
+      }
+    }
+    float dla[DT];
+    const int64_t row = idx[m];
+#pragma unroll
+    for (int a = 0; a < DT; ++a) {
+      float s = acc[a];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float c = act_f(s + __ldg(seg + fin * DT + a), lastact);
+      const float r = c - __ldg(target + row * DT + a);
+      float dl;
+      if (DT == 1) {
+        lsum += (double)r * (double)r;
+        dl = (float)(2.0 * (double)r / Bglobal);
+      } else {
+        const float wa = __ldg(wl + a);
+        const float zz = r * wa;
+        lsum += (double)(zz * zz);
+        dl = ((2.0f * zz) * invB) * wa;
+      }
+      dl *= dact_f(c, lastact);
+      dla[a] = dl;
+      if (lane == 0) {
+        chi[m * DT + a] = c;
+        delta[m * DT + a] = dl;
+        __nv_bfloat16 h0, l0;
+        split1(dl, h0, l0);
+        dl_hi[m * ld_dl + a] = h0;
+        dl_lo[m * ld_dl + a] = l0;
+      }
+    }
+    // ---- delta_{L-1} = (delta_L W^T) .* act'(z); columns >= fin (ones column, padding) are written as 0
+    uint4 *qh = reinterpret_cast<uint4 *>(out_hi + m * ldo);
+    uint4 *ql = reinterpret_cast<uint4 *>(out_lo + m * ldo);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int k8 = lane + 32 * j;
+      if ((int64_t)k8 * 8 < ldo) {
+        uint4 h = make_uint4(0, 0, 0, 0), l = h;
+        if (k8 * 8 < fin) {
+          h = __ldg(ph + k8);
+          l = __ldg(pl + k8);
+        }
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+        uint32_t oh[4], ol[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float g[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int k = k8 * 8 + 2 * e + q;
+            float s = 0.f;
+            if (k < fin) {
+#pragma unroll
+              for (int a = 0; a < DT; ++a) s = fmaf(dla[a], __ldg(seg + k * DT + a), s);
+              const float z = q == 0 ? bflo(hw[e]) + bflo(lw[e]) : bfhi(hw[e]) + bfhi(lw[e]);
+              s *= dact_f(z, act);
+            }
+            g[q] = s;
+          }
+          __nv_bfloat16 h0, l0, h1, l1;
+          split1(g[0], h0, l0);
+          split1(g[1], h1, l1);
+          oh[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          ol[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        qh[k8] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+        ql[k8] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+      }
+    }
+    for (int k8 = lane + 32 * NCH; (int64_t)k8 * 8 < ldo; k8 += 32) {  // padding past 256 * NCH columns
+      qh[k8] = make_uint4(0, 0, 0, 0);
+      ql[k8] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  // every lane of a warp carries the same lsum; lane 0 speaks for the warp
+  if (lane == 0) sh[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += sh[k];
+    partials[blockIdx.x] = s;
+    __threadfence();
+    const unsigned int prev = atomicAdd(ticket, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) s += ((volatile double *)partials)[b];
+    const float hi = (float)s;
+    const float lo = (hi == hi && fabsf(hi) != INFINITY) ? (float)(s - (double)hi) : 0.f;
+    packed_tail[0] = hi;
+    packed_tail[1] = lo;
+    *ticket = 0u;
+  }
+}
+
 }  // namespace
+
 
 void launch_f32_to_split(Ctx &c, const float *in, int64_t rows, int cols, __nv_bfloat16 *hi, __nv_bfloat16 *lo,
                          int64_t ld) {
@@ -253,6 +402,54 @@ void launch_thin_dgrad(Ctx &c, const float *delta, int64_t M, int d, const float
   int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c.num_sms * 16);
   c.timer.begin(KC_TRAIN_EW, c.stream);
   thin_dgrad_kernel<<<grid, 256, 0, c.stream>>>(delta, M, d, seg, fin, z_hi, z_lo, ldz, act, out_hi, out_lo, ldo);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_TRAIN_EW);
+}
+
+bool thin_head_eligible(const Ctx &c) {
+  const int fin = c.cfg.widths[c.L - 1];
+  return c.d >= 1 && c.d <= 4 && fin <= 2048;
+}
+
+template <int NCH>
+static void thin_head_go(Ctx &c, int grid, const __nv_bfloat16 *z_hi, const __nv_bfloat16 *z_lo, int64_t M, int fin,
+                         int64_t ldz, const float *seg, const float *target, const int64_t *idx, const float *wl,
+                         double Bglobal, float *chi, float *delta, __nv_bfloat16 *dl_hi, __nv_bfloat16 *dl_lo, int ld_dl,
+                         __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ldo, double *partials,
+                         unsigned int *ticket, float *packed_tail) {
+  const int d = c.d, act = c.cfg.activation, lact = c.cfg.last_activation;
+#define IK_HEAD(DT)                                                                                                   \
+  thin_head_kernel<NCH, DT><<<grid, 256, 0, c.stream>>>(z_hi, z_lo, M, fin, ldz, seg, d, act, lact, target, idx, wl,   \
+                                                        Bglobal, chi, delta, dl_hi, dl_lo, ld_dl, out_hi, out_lo, ldo, \
+                                                        partials, ticket, packed_tail)
+  switch (d) {
+    case 1: IK_HEAD(1); break;
+    case 2: IK_HEAD(2); break;
+    case 3: IK_HEAD(3); break;
+    default: IK_HEAD(4); break;
+  }
+#undef IK_HEAD
+}
+
+void launch_thin_head(Ctx &c, const __nv_bfloat16 *z_hi, const __nv_bfloat16 *z_lo, int64_t M, int fin, int64_t ldz,
+                      const float *seg, const float *target, const int64_t *idx, const float *wl, double Bglobal,
+                      float *chi, float *delta, __nv_bfloat16 *dl_hi, __nv_bfloat16 *dl_lo, int ld_dl,
+                      __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ldo, double *partials,
+                      unsigned int *ticket, float *packed_tail) {
+  if (M <= 0) return;
+  // the grid is a function of M only, so the order of the loss partials is reproducible
+  const int grid = (int)std::min<int64_t>((M + 7) / 8, 1024);
+  c.timer.begin(KC_TRAIN_EW, c.stream);
+  if (fin <= 512)
+    thin_head_go<2>(c, grid, z_hi, z_lo, M, fin, ldz, seg, target, idx, wl, Bglobal, chi, delta, dl_hi, dl_lo, ld_dl,
+                    out_hi, out_lo, ldo, partials, ticket, packed_tail);
+  else if (fin <= 1024)
+    thin_head_go<4>(c, grid, z_hi, z_lo, M, fin, ldz, seg, target, idx, wl, Bglobal, chi, delta, dl_hi, dl_lo, ld_dl,
+                    out_hi, out_lo, ldo, partials, ticket, packed_tail);
+  else
+    thin_head_go<8>(c, grid, z_hi, z_lo, M, fin, ldz, seg, target, idx, wl, Bglobal, chi, delta, dl_hi, dl_lo, ld_dl,
+                    out_hi, out_lo, ldo, partials, ticket, packed_tail);
   c.timer.end(c.stream);
   IK_CUDA(cudaGetLastError());
   c.count_launch(KC_TRAIN_EW);

@@ -163,6 +163,26 @@ def test_record_featurizer_split_output_other_atom_counts(pkg, oracle, A):
     assert np.allclose(records(pkg.koopman(iso)), k_ref, rtol=TOL_CHI, atol=5e-5)
 
 
+@pytest.mark.parametrize("widths,target", [([231, 256, 320, 1], "shiftscale"), ([231, 512, 264, 3], "isa"),
+                                            ([231, 256, 1032, 2], "isa")])
+def test_fused_thin_head_matches_separate_kernels(pkg, oracle, monkeypatch, widths, target):
+    # training step: thin_head_kernel (last layer + loss + both backward products in one pass) against the
+    # thin_forward / loss_delta / f32_to_split / thin_dgrad sequence (ISOKANN_TC_NO_HEAD=1)
+    w = wide(pkg, widths)
+    N, K = 700, 2
+    xs, ys = pkg.synthetic.make_data(w, N, K)
+    flat = oracle.flatten_params(oracle_model(oracle, w.widths, True, 5))
+    perms = pkg.synthetic.make_perms(w, N, 3)
+    fused = make_iso(pkg, w, xs, ys, flat, opt="adam", target=target, minibatch=250, gemm="tc")
+    monkeypatch.setenv("ISOKANN_TC_NO_HEAD", "1")
+    plain = make_iso(pkg, w, xs, ys, flat, opt="adam", target=target, minibatch=250, gemm="tc")
+    pkg.run_(fused, 3, perms=perms)
+    pkg.run_(plain, 3, perms=perms)
+    assert np.allclose(fused.losses, plain.losses, rtol=1e-10)       # same terms, another summation order
+    assert np.array_equal(fused.engine.download_params(), plain.engine.download_params())
+    assert fused.engine.stats()["kernel_launches"] < plain.engine.stats()["kernel_launches"]
+
+
 def test_featurizer_gemm_overlap_is_bit_identical(pkg, oracle, monkeypatch):
     # ISOKANN_OVERLAP=1: the featurizer of chunk i+1 runs on a second stream beside the GEMMs of chunk i
     w = wide(pkg, [231, 256, 256, 1])
