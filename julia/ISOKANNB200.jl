@@ -204,6 +204,38 @@ function ISOKANN.addcoords!(iso::Iso{<:B200Model}, coords::AbstractMatrix)
     nothing
 end
 
+# iso.data = iso.data[end-cutoff+1:end] (run_kde!, src/iso.jl:288-290): drop the oldest points on the device
+function cutoff!(iso::Iso{<:B200Model}, cutoff::Integer)
+    length(iso.data) > cutoff || return nothing
+    check(iso.model, ccall((:isokann_keep_last, LIB), Int32, (Ptr{Cvoid}, Int64), iso.model.handle, cutoff))
+    iso.data = iso.data[end-cutoff+1:end]
+    iso.model.N = cutoff
+    nothing
+end
+
+# model(propfeatures(data)) for resample_kde / chistratcoords (src/simulation.jl:199-207,227-228): (d, K, N)
+function propchis(iso::Iso{<:B200Model})
+    m = iso.model
+    out = Array{Float32}(undef, ISOKANN.outputdim(m.chain), ISOKANN.nk(iso.data), m.N)
+    check(m, ccall((:isokann_chis_prop, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}), m.handle, out)); out
+end
+
+"""Upload that overlaps the next Koopman pass: ys, then xs, stream in behind the call (keep both arrays alive and
+unmodified until results computed from them have come back; page-lock them for a truly asynchronous copy)"""
+function setdata_async!(m::B200Model, xs::Matrix{Float32}, ys::Array{Float32,3}; offset=0, nlocal=size(ys, 3))
+    D, K, _ = size(ys)
+    check(m, ccall((:isokann_set_data_async, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64, Int64, Int64, Int64, Int64),
+        m.handle, xs, ys, D, K, size(xs, 2), offset, nlocal))
+    m.N = size(xs, 2)
+end
+
+# One Julia process per GPU: rank 0 creates the id, the host broadcasts the 128 bytes (MPI / Distributed), every
+# rank joins before its first setdata!; ys then holds only this rank's contiguous slice of the start points.
+unique_id() = (id = Vector{UInt8}(undef, 128); ccall((:isokann_comm_get_unique_id, LIB), Int32, (Ptr{UInt8},), id); id)
+comm_init!(m::B200Model, world::Integer, rank::Integer, id::Vector{UInt8}) =
+    check(m, ccall((:isokann_comm_init, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), m.handle, world, rank, id))
+
 """run!(iso, n, epochs) without host round trips (src/iso.jl:72-94)"""
 function run_fused!(iso::Iso{<:B200Model}, n=1, epochs=1)
     m = iso.model
