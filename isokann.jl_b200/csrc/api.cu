@@ -77,11 +77,13 @@ int32_t guarded(isokann_ctx *ctx, Fn &&fn) {
     return ISOKANN_OK;
   } catch (const ik::Error &e) {
     ctx->err = e.msg;
-    // leave the device in a clean state for the next call
+    // leave the device and the timer in a clean state for the next call
     if (e.code == ISOKANN_ERR_CUDA) cudaGetLastError();
+    ctx->timer.open.clear();
     return e.code;
   } catch (const std::exception &e) {
     ctx->err = e.what();
+    ctx->timer.open.clear();
     return ISOKANN_ERR_STATE;
   }
 }
@@ -503,10 +505,15 @@ void compute_koopman(Ctx &c) {
         const int64_t last = std::min<int64_t>((n0 + ns - 1) / c.ys_chunk_pts, c.ys_chunks_pending - 1);
         IK_CUDA(cudaStreamWaitEvent(t.feat_stream, c.ys_events[(size_t)last], 0));
       }
-      std::swap(c.stream, t.feat_stream);
-      launch_featurize_split(c, c.ys + n0 * c.K * c.D, nullptr, 0, ns * c.K, pairs, c.ln, bufs[b]->hi.p, bufs[b]->lo.p,
-                             t.wp[0]);
-      std::swap(c.stream, t.feat_stream);
+      {
+        struct SwapBack {  // launch on the featurizer stream; restore the context's stream even if the launch throws
+          cudaStream_t &a, &b;
+          ~SwapBack() { std::swap(a, b); }
+        } back{c.stream, t.feat_stream};
+        std::swap(c.stream, t.feat_stream);
+        launch_featurize_split(c, c.ys + n0 * c.K * c.D, nullptr, 0, ns * c.K, pairs, c.ln, bufs[b]->hi.p,
+                               bufs[b]->lo.p, t.wp[0]);
+      }
       IK_CUDA(cudaEventRecord(t.feat_done[b], t.feat_stream));
       IK_CUDA(cudaStreamWaitEvent(c.stream, t.feat_done[b], 0));
       forward_rows_tc(c, nullptr, nullptr, 0, ns * c.K, true, false, bufs[b]);
@@ -813,9 +820,14 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
                        c.grads.p + c.off_b[0]);
   } else {
     const bool head = c.tc && !c.tc_no_head && thin_head_eligible(c);
-    c.head_fused_now = head;
-    forward_rows(c, c.xs, c.perm_dev.p, s0, Bloc, true, true);
-    c.head_fused_now = false;
+    {
+      struct Reset {  // the flag must not survive an error thrown inside the forward pass
+        bool &f;
+        ~Reset() { f = false; }
+      } reset{c.head_fused_now};
+      c.head_fused_now = head;
+      forward_rows(c, c.xs, c.perm_dev.p, s0, Bloc, true, true);
+    }
     c.delta_a.ensure((size_t)Bloc * c.maxw);
     c.delta_b.ensure((size_t)Bloc * c.maxw);
     float *cur = c.delta_a.p, *other = c.delta_b.p;
