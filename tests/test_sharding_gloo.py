@@ -59,7 +59,10 @@ def _worker(rank, world, port, out_dir):
 
 def test_world2_matches_single_process(tmp_path, pkg, oracle):
     import torch.multiprocessing as mp
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as sk:                         # a port that is free right now
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0 = np.load(tmp_path / "rank0.npz")
     r1 = np.load(tmp_path / "rank1.npz")
