@@ -8,17 +8,34 @@ One "step" is one body of the reference's run! loop (src/iso.jl:72-94): Koopman 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config c5] [--impl reference]
 
 N > 1 is launched by torchrun, one rank per GPU; start points are sharded over ranks
-(strong scaling: the workload is fixed).  Prints ONE JSON line on rank 0.
+(strong scaling: the workload is fixed).  Prints ONE JSON line on rank 0.  The headline (`value`, `e2e`,
+`roofline`) is BASELINE config 5; `configs` carries configs 2, 3 and 4 (ISA and PseudoInv) measured the same way.
 """
 from __future__ import annotations
 
+import os
+import sys
+
+
+def _affinity_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # the CPU arm uses every host core it may run on, whatever the launcher exported (torchrun sets
+    # OMP_NUM_THREADS=1): BLAS thread pools read these variables when numpy is imported
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_affinity_threads())
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
+import zlib
 from pathlib import Path
 
 import numpy as np
@@ -28,6 +45,8 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "koopman_samples_per_s_per_isokann_iteration"
 UNIT = "samples/s"
+DTYPE_NOTE = ("fp32 storage and accumulation; wide Dense layers multiply split-bf16 operands on tcgen05 (3 MMAs per "
+              "product: hi*hi + hi*lo + lo*hi, lo*lo dropped), narrow layers run FP32 FFMA")
 
 
 def parse():
@@ -40,10 +59,13 @@ def parse():
     ap.add_argument("--N", type=int, default=None)
     ap.add_argument("--K", type=int, default=None)
     ap.add_argument("--minibatch", type=int, default=None)
+    ap.add_argument("--target", default=None, choices=["shiftscale", "isa", "pinv"])
     ap.add_argument("--gemm", default="auto", choices=["auto", "fp32", "tc"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the c2/c3/c4 entries of `configs`")
     ap.add_argument("--profile", action="store_true",
-                    help="short run for ncu: no e2e / CPU baseline, warm-up not forced to 3; never a bench value")
+                    help="short run for ncu: no e2e / CPU baseline / extra configs, warm-up not forced to 3; "
+                         "never a bench value")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="start points in the CPU baseline sample")
     return ap.parse_args()
@@ -57,10 +79,11 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
 
 
-def workload_config(w, N, K, B, extra=None):
+def workload_config(w, N, K, B, target, extra=None):
     cfg = {"workload": f"{w.name}: {w.n_atoms}-atom pairdist featurizer F={w.F}, pairnet {w.widths}, N={N}, K={K}, "
-                       f"{w.target} target, {w.opt}, minibatch={B}",
-           "N": N, "K": K, "minibatch": B, "widths": list(w.widths), "target": w.target, "optimiser": w.opt,
+                       f"{target} target, {w.opt}, minibatch={B}",
+           "N": N, "K": K, "minibatch": B, "widths": list(w.widths), "target": target, "optimiser": w.opt,
+           "arithmetic": DTYPE_NOTE,
            "l2": "inputs (coords of K*N samples) larger than the 126 MB L2" if N * K * w.D * 4 > 126e6
                  else "inputs fit in L2; steady-state iteration"}
     if extra:
@@ -71,7 +94,15 @@ def workload_config(w, N, K, B, extra=None):
 # ---------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference's run! on the host cores, bounded sample
 # ---------------------------------------------------------------------------------------------
-def cpu_iteration_sample(pkg, w, Ns, K, B, steps, warmup):
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(p.get("num_threads", 1)) for p in threadpool_info()] or [1])
+    except Exception:
+        return None
+
+
+def cpu_iteration_sample(pkg, w, Ns, K, B, steps, warmup, target):
     """time `steps` oracle iterations on Ns start points (cached Float32 features exactly as the
     reference does, src/simulation.jl:112); returns (samples/s, seconds per step)"""
     import oracle
@@ -85,31 +116,23 @@ def cpu_iteration_sample(pkg, w, Ns, K, B, steps, warmup):
     cfg = oracle.OptConfig(kind=w.opt)
     st = oracle.opt_init(cfg, oracle.num_params(m))
     perms = pkg.synthetic.make_perms(w, Ns, warmup + steps)
-    kw = {}
     for i in range(warmup):
-        oracle.run(m, xsf, ysf, cfg, st, 1, B, [perms[i]], w.target, **kw)
+        oracle.run(m, xsf, ysf, cfg, st, 1, B, [perms[i]], target)
     t0 = time.perf_counter()
     for i in range(steps):
-        oracle.run(m, xsf, ysf, cfg, st, 1, B, [perms[warmup + i]], w.target, **kw)
+        oracle.run(m, xsf, ysf, cfg, st, 1, B, [perms[warmup + i]], target)
     dt = (time.perf_counter() - t0) / steps
     return Ns * K / dt, dt
 
 
 def cpu_sample_size(w, N, K, requested):
+    """start points of the CPU sample: all of N when one iteration is below ~2e12 flop, else N/64"""
     if requested > 0:
         return min(N, requested)
-    # aim at ~10-30 s of CPU work for warmup+steps iterations: ~2e12 flop per iteration
     flop_per_start = 2.0 * w.macs() * (K + 3)
-    ns = int(2.0e12 / max(flop_per_start, 1.0))
-    ns = max(256, min(N, ns))
-    return ns
-
-
-def n_cores():
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
+    if flop_per_start * N <= 2.0e12:
+        return N
+    return max(256, N // 64)
 
 
 def run_reference(args, pkg):
@@ -120,20 +143,25 @@ def run_reference(args, pkg):
     N = args.N or w.N
     K = args.K or w.K
     B = args.minibatch if args.minibatch is not None else w.minibatch
+    target = args.target or w.target
     Ns = cpu_sample_size(w, N, K, args.cpu_sample)
     Bs = min(B, Ns) if B else 0
-    steps, warm = max(1, args.steps), max(1, min(args.warmup, 1))
-    val, dt = cpu_iteration_sample(pkg, w, Ns, K, Bs, steps, warm)
-    sample = (f"{Ns} of {N} start points (x{K} Koopman samples), one full iteration each step, minibatch {Bs}; "
-              f"throughput is per-sample so it carries to the full N at fixed minibatch")
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    val, dt = cpu_iteration_sample(pkg, w, Ns, K, Bs, steps, warm, target)
+    threads = blas_threads()
+    sample = (f"{Ns} of {N} start points (x{K} Koopman samples) = 1/{N / Ns:.0f} of the workload, one full iteration "
+              f"each step, minibatch min(B, Ns) = {Bs}; per-sample throughput, i.e. scaled linearly to the full N")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(w, N, K, B, {"note": "CPU restatement of reference run! (Flux semantics) in numpy/"
-                                               "OpenBLAS; Julia is not installable here, so the reference itself "
-                                               "cannot be timed"}),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": n_cores(), "kind": "port", "sample": sample},
+        "config": workload_config(w, N, K, B, target,
+                                  {"note": "CPU restatement of reference run! (Flux semantics) in numpy/OpenBLAS: "
+                                           "multi-threaded BLAS, single-threaded broadcasts, like Flux on the CPU; "
+                                           "Julia is not installable here, so the reference itself cannot be timed",
+                                   "arithmetic": "fp32 numpy (OpenBLAS sgemm)"}),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": _affinity_threads(), "threads": threads, "kind": "port",
+                         "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,8 +223,13 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
+BLOCK_PTS = 4096   # start points per noise block of the synthetic ys
+
+
 def device_data(pkg, w, N, K, off, n_loc, device):
-    """synthetic coordinates generated on the device: xs (N, D) on every rank, ys (n_loc, K, D) shard"""
+    """synthetic coordinates generated on the device: xs (N, D) on every rank, ys (n_loc, K, D) shard.  The noise of
+    ys is drawn per block of 4096 start points from a seed that depends on the block only, so every world size
+    sees the same data set and the `check` blocks of the 1/2/4/8-GPU lines are comparable."""
     import torch
     rng = np.random.default_rng(w.seed)
     if w.featurizer == "identity":
@@ -210,14 +243,135 @@ def device_data(pkg, w, N, K, off, n_loc, device):
     g.manual_seed(1234 + w.seed)
     which = torch.randint(0, len(states), (N,), generator=g, device=device)
     xs = base[which] + 0.05 * torch.randn((N, w.D), generator=g, device=device)
-    g2 = torch.Generator(device=device)
-    g2.manual_seed(99 + w.seed + off)
     ys = torch.empty((n_loc, K, w.D), dtype=torch.float32, device=device)
-    step = max(1, (1 << 26) // (K * w.D))
-    for s in range(0, n_loc, step):
-        e = min(n_loc, s + step)
-        ys[s:e] = xs[off + s:off + e, None, :] + 0.03 * torch.randn((e - s, K, w.D), generator=g2, device=device)
+    g2 = torch.Generator(device=device)
+    for b in range(off // BLOCK_PTS, (off + n_loc + BLOCK_PTS - 1) // BLOCK_PTS if n_loc > 0 else 0):
+        g2.manual_seed(1_000_003 * (w.seed + 1) + b)
+        noise = 0.03 * torch.randn((BLOCK_PTS, K, w.D), generator=g2, device=device)
+        s, e = max(off, b * BLOCK_PTS), min(off + n_loc, (b + 1) * BLOCK_PTS, N)
+        ys[s - off:e - off] = xs[s:e, None, :] + noise[s - b * BLOCK_PTS:e - b * BLOCK_PTS]
     return xs.contiguous(), ys
+
+
+class Runner:
+    """one workload on this rank's GPU: engine + resident synthetic data + timing helpers"""
+
+    def __init__(self, pkg, args, w, N, K, B, target, world, rank, local, uid):
+        import torch
+        self.torch = torch
+        self.pkg, self.w, self.N, self.K, self.B, self.target = pkg, w, N, K, B, target
+        self.world, self.rank, self.local = world, rank, local
+        self.device = torch.device("cuda", local)
+        self.off, self.n_loc = pkg.parallel.shard_range(N, world, rank)
+        rngp = np.random.default_rng(w.seed + 1)
+        model = pkg.densenet(w.widths, layernorm=w.layernorm, rng=rngp)
+        rule = pkg.AdamRegularized() if w.opt == "adam" else pkg.NesterovRegularized()
+        self.eng = pkg.Engine(model, rule, "allpairs" if w.featurizer == "allpairs" else "identity", w.n_atoms, None,
+                              device=local, gemm=args.gemm)
+        if world > 1:
+            self.eng.comm_init(world, rank, uid)
+        self.xs, self.ys = device_data(pkg, w, N, K, self.off, self.n_loc, self.device)
+        torch.cuda.synchronize()
+        self.eng.set_data_dev(self.xs, self.ys, w.D, K, N, self.off, self.n_loc)
+        self.ext = torch.cuda.ExternalStream(self.eng.stream(), device=self.device)
+
+    def barrier(self):
+        import torch.distributed as dist
+        self.eng.synchronize()
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """device time of `steps` calls of fn, bracketed by barrier+sync, CUDA events on the library's stream,
+        max over ranks"""
+        import torch.distributed as dist
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        with torch.cuda.stream(self.ext):
+            e0.record()
+        for i in range(steps):
+            fn(i)
+        with torch.cuda.stream(self.ext):
+            e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def iterate(self, perm):
+        return self.eng.iterate(self.target, 1, 1, self.B, perm)
+
+    def check(self, losses):
+        """numbers that let the 1/2/4/8-GPU lines be compared: the data set, the initial weights and the
+        permutations are identical for every world size, so these agree up to fp32 summation order"""
+        import torch.distributed as dist
+        flat = self.eng.download_params()
+        k = self.eng.koopman()
+        crc = zlib.crc32(flat.tobytes())
+        same = True
+        if self.world > 1:
+            t = self.torch.tensor([crc], dtype=self.torch.int64, device=self.device)
+            all_t = [self.torch.zeros_like(t) for _ in range(self.world)]
+            dist.all_gather(all_t, t)
+            same = all(int(x.item()) == crc for x in all_t)
+        return {"first_loss": float(losses[0]), "last_loss": float(losses[-1]),
+                "param_l2": float(np.linalg.norm(flat.astype(np.float64))),
+                "param_crc32": int(crc), "ranks_hold_identical_params": bool(same),
+                "kchi_min": float(k.min()), "kchi_max": float(k.max()), "kchi_mean": float(k.astype(np.float64).mean()),
+                "after": f"{len(losses)} warm-up+timed iterations from the seeded initial weights"}
+
+    def close(self):
+        self.eng.close()
+        del self.xs, self.ys
+        self.torch.cuda.empty_cache()
+
+
+def measure(r: Runner, nsteps, nwarm, perms, with_clocks):
+    """resident-data throughput, then the same steps again with CUDA events around every kernel launch"""
+    losses = []
+    for i in range(nwarm):
+        losses.extend(r.iterate(perms[i]))
+    r.eng.reset_stats()
+    sampler = ClockSampler(r.local) if with_clocks and r.rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = r.timed(lambda i: losses.extend(r.iterate(perms[nwarm + i])), nsteps)
+    clocks = sampler.stop() if sampler else None
+    launches = r.eng.stats()["kernel_launches"]
+    chk = r.check(losses)
+    r.eng.reset_stats()
+    r.eng.enable_timing(True)
+    r.timed(lambda i: r.iterate(perms[nwarm + i]), nsteps)
+    st = r.eng.stats()
+    r.eng.enable_timing(False)
+    return ms, clocks, launches, chk, st
+
+
+def phase_dict(st, nsteps):
+    return ({"koopman": st["ms_koopman_total"] / nsteps, "target": st["ms_target_total"] / nsteps,
+             "train": st["ms_train_total"] / nsteps},
+            {"featurize": st["ms_featurize"] / nsteps, "gemm": st["ms_gemm"] / nsteps,
+             "reduce": st["ms_reduce"] / nsteps, "train_elementwise": st["ms_train_elementwise"] / nsteps,
+             "optimiser": st["ms_optimiser"] / nsteps, "nccl": st["ms_nccl"] / nsteps})
+
+
+def hbm_roofline(w, N, K, ms_iter, pk, nd):
+    """whole-iteration HBM roofline of the narrow-net configs: BASELINE.md section 4 minimum bytes
+    4*D*N*(K+1) (+ 4*D*N for the extra chi(xs) pass of the N-D targets), coordinates read once per pass"""
+    byts = 4.0 * w.D * N * (K + 1 + (1 if nd else 0))
+    ach = byts / (ms_iter * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "whole iteration (featurize+MLP fused passes over the coordinates)",
+            "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+            "algorithmic_bytes": byts, "peak_source": pk["src"]}
+
+
+EXTRA = [("c2", "c2", None), ("c3", "c3", None), ("c4_isa", "c4", "isa"), ("c4_pinv", "c4", "pinv")]
 
 
 def run_b200(args, pkg):
@@ -238,97 +392,65 @@ def run_b200(args, pkg):
     N = args.N or w.N
     K = args.K or w.K
     B = args.minibatch if args.minibatch is not None else w.minibatch
-    off, n_loc = pkg.parallel.shard_range(N, world, rank)
-
-    rngp = np.random.default_rng(w.seed + 1)
-    model = pkg.densenet(w.widths, layernorm=w.layernorm, rng=rngp)
-    rule = pkg.AdamRegularized() if w.opt == "adam" else pkg.NesterovRegularized()
-    eng = pkg.Engine(model, rule, "allpairs" if w.featurizer == "allpairs" else "identity", w.n_atoms, None,
-                     device=local, gemm=args.gemm)
-    if world > 1:
-        uid = pkg.parallel.broadcast_unique_id(rank)
-        eng.comm_init(world, rank, uid)
-    xs, ys = device_data(pkg, w, N, K, off, n_loc, device)
-    torch.cuda.synchronize()
-    eng.set_data_dev(xs, ys, w.D, K, N, off, n_loc)
+    target = args.target or w.target
     nsteps, nwarm = args.steps, (args.warmup if args.profile else max(3, args.warmup))
     if args.profile:
-        args.no_e2e = args.no_cpu_baseline = True
+        args.no_e2e = args.no_cpu_baseline = args.no_extra = True
+    pk = peaks()
+
+    def new_uid():
+        return pkg.parallel.broadcast_unique_id(rank) if world > 1 else None
+
+    r = Runner(pkg, args, w, N, K, B, target, world, rank, local, new_uid())
+    eng, xs, ys, off, n_loc = r.eng, r.xs, r.ys, r.off, r.n_loc
     perms = pkg.synthetic.make_perms(w, N, nwarm + nsteps)
-    opts = {}
-
-    def barrier():
-        eng.synchronize()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    ext = torch.cuda.ExternalStream(eng.stream(), device=device)
-
-    def timed(fn, steps):
-        """device time of `steps` calls of fn, bracketed by barrier+sync, CUDA events on the library's stream"""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        with torch.cuda.stream(ext):
-            e0.record()
-        for i in range(steps):
-            fn(i)
-        with torch.cuda.stream(ext):
-            e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    # ---- resident-data throughput (`value`): no per-kernel timers in this pass ----
-    for i in range(nwarm):
-        eng.iterate(w.target, 1, 1, B, perms[i], **opts)
-    eng.reset_stats()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms = timed(lambda i: eng.iterate(w.target, 1, 1, B, perms[nwarm + i], **opts), nsteps)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = eng.stats()["kernel_launches"]
+    ms, clocks, launches, chk, st = measure(r, nsteps, nwarm, perms, True)
     value = N * K * nsteps / (ms * 1e-3)
-    # ---- same steps again with CUDA events around every kernel launch (roofline, phase split) ----
-    eng.reset_stats()
-    eng.enable_timing(True)
-    timed(lambda i: eng.iterate(w.target, 1, 1, B, perms[nwarm + i], **opts), nsteps)
-    st = eng.stats()
-    eng.enable_timing(False)
 
     # ---- end to end through the public API with HOST buffers ----
     e2e = None
     if not args.no_e2e:
-        xs_h = torch.empty(xs.shape, dtype=torch.float32, pin_memory=True)
-        ys_h = torch.empty(ys.shape, dtype=torch.float32, pin_memory=True)
-        xs_h.copy_(xs)
-        ys_h.copy_(ys)
-        torch.cuda.synchronize()
-        xs_j, ys_j = xs_h.numpy().T, ys_h.numpy().T          # Julia-shaped (D, N), (D, K, n_loc) views
+        # plain (pageable) numpy arrays, as a Julia caller would hand over: the library page-locks them itself
+        xs_j = np.asfortranarray(xs.cpu().numpy().T)          # Julia-shaped (D, N)
+        ys_j = np.asfortranarray(ys.cpu().numpy().T)          # (D, K, n_loc)
         nparams = eng.P
 
         def e2e_step(i):
             # SimulationData upload + run!(iso, 1) + the loss and cpu(iso) (the updated model) back on the host
             eng.set_data_async(xs_j, ys_j, n_offset=off, n_local=n_loc)
-            eng.iterate(w.target, 1, 1, B, perms[i % len(perms)], **opts)
+            eng.iterate(target, 1, 1, B, perms[i % len(perms)])
             eng.download_params()
         for i in range(2):
             e2e_step(i)
-        ms_e = timed(e2e_step, nsteps)
+        ms_e = r.timed(e2e_step, nsteps)
         # whole job, all ranks together: every rank uploads its shard of ys, its own rows of xs (the other rows come
         # from the peers over NVLink) and the permutation; every rank reads the loss and the parameters back
         h2d = 4 * (xs.numel() + N * K * xs.shape[1]) + 8 * N * world
         d2h = (8 + 4 * nparams) * world
         e2e = {"value": N * K * nsteps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / nsteps,
-               "call": "isokann_set_data_async (pinned host xs, ys streamed in behind the Koopman pass) + run!(iso,1) + loss and cpu(iso) parameters to host"}
-        eng.set_data_dev(xs, ys, w.D, K, N, off, n_loc)
+               "call": "isokann_set_data_async (pageable host xs/ys, page-locked by the library, ys streamed in "
+                       "behind the Koopman pass) + run!(iso,1) + loss and cpu(iso) parameters to host"}
+        eng.release_host_buffers()
+        del xs_j, ys_j
+    r.close()
+
+    # ---- the other BASELINE configs, measured the same way (device-timed, resident data) ----
+    extra = {}
+    if not args.no_extra and args.config == "c5" and args.N is None:
+        for key, cname, tgt in EXTRA:
+            we = pkg.synthetic.WORKLOADS[cname]
+            te = tgt or we.target
+            re_ = Runner(pkg, args, we, we.N, we.K, we.minibatch, te, world, rank, local, new_uid())
+            pe = pkg.synthetic.make_perms(we, we.N, 3 + 5)
+            ms_x, _, launches_x, chk_x, st_x = measure(re_, 5, 3, pe, False)
+            ph, kk = phase_dict(st_x, 5)
+            extra[key] = {"config": workload_config(we, we.N, we.K, we.minibatch, te),
+                          "ms_per_iteration": ms_x / 5, "value": we.N * we.K * 5 / (ms_x * 1e-3), "unit": UNIT,
+                          "steps": 5, "warmup": 3, "gpu_launches": int(launches_x),
+                          "roofline": hbm_roofline(we, we.N, we.K, ms_x / 5, pk, te != "shiftscale"),
+                          "phase_ms_per_step": ph, "kernel_ms_per_step": kk, "check": chk_x}
+            re_.close()
 
     if rank != 0:
         if world > 1:
@@ -336,7 +458,6 @@ def run_b200(args, pkg):
             dist.destroy_process_group()
         return
 
-    pk = peaks()
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists() and N == w.N and K == w.K:
@@ -354,12 +475,7 @@ def run_b200(args, pkg):
                         "executed_tflops = 3*achieved is what the tensor pipe runs; traffic = mean dram bytes per "
                         "launch from profiles/traffic.json (ncu)"}
     else:
-        ach = st["featurize_bytes"] / (st["ms_featurize"] * 1e-3) / 1e9 if st["ms_featurize"] > 0 else 0.0
-        roof = {"bound": "hbm", "kernel": "featurizer (pair distances + LayerNorm)", "achieved": ach,
-                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic,
-                "peak_source": pk["src"], "launches": st["n_featurize_launches"],
-                "avg_launch_ms": st["ms_featurize"] / max(1, st["n_featurize_launches"]),
-                "note": "algorithmic 4*(D+F) bytes per record / CUDA-event time of the featurizer launches"}
+        roof = hbm_roofline(w, N, K, ms / nsteps, pk, target != "shiftscale")
     # the other kernel north_star asks a roofline figure for: the featurizer against measured HBM bandwidth
     fz = None
     if st["ms_featurize"] > 0 and st["featurize_bytes"] > 0:
@@ -368,27 +484,25 @@ def run_b200(args, pkg):
               "launches": st["n_featurize_launches"],
               "note": "algorithmic 4*(D+F) bytes per record / CUDA-event time of the featurizer launches, timed inside "
                       "the step (power-capped SM clock); split bf16 output moves 4*(D+ld) bytes, ld = F padded to 64"}
+    ph, kk = phase_dict(st, nsteps)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": nsteps, "warmup": nwarm,
         "ms_per_step": ms / nsteps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(w, N, K, B, {"parallelism": f"start points sharded over {world} GPU(s)",
-                                               "gemm": args.gemm}),
+        "config": workload_config(w, N, K, B, target, {"parallelism": f"start points sharded over {world} GPU(s)",
+                                                       "gemm": args.gemm}),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roof, "roofline_featurizer": fz,
-        "phase_ms_per_step": {"koopman": st["ms_koopman_total"] / nsteps, "target": st["ms_target_total"] / nsteps,
-                              "train": st["ms_train_total"] / nsteps},
-        "kernel_ms_per_step": {"featurize": st["ms_featurize"] / nsteps, "gemm": st["ms_gemm"] / nsteps,
-                               "reduce": st["ms_reduce"] / nsteps, "train_elementwise": st["ms_train_elementwise"] / nsteps,
-                               "optimiser": st["ms_optimiser"] / nsteps, "nccl_allreduce": st["ms_nccl"] / nsteps},
+        "roofline": roof, "roofline_featurizer": fz, "check": chk,
+        "phase_ms_per_step": ph, "kernel_ms_per_step": kk, "configs": extra or None,
     }
     if not args.no_cpu_baseline and world == 1:
         Ns = cpu_sample_size(w, N, K, args.cpu_sample)
         Bs = min(B, Ns) if B else 0
-        val, dt = cpu_iteration_sample(pkg, w, Ns, K, Bs, 1, 1)
-        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": n_cores(), "kind": "port",
-                                "sample": f"{Ns} of {N} start points (x{K} Koopman samples), one iteration, "
-                                          f"minibatch {Bs}, {dt:.1f} s; per-sample throughput"}
+        val, dt = cpu_iteration_sample(pkg, w, Ns, K, Bs, 1, 1, target)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": _affinity_threads(), "threads": blas_threads(),
+                                "kind": "port",
+                                "sample": f"{Ns} of {N} start points (x{K} Koopman samples), one iteration after one "
+                                          f"warm-up, minibatch {Bs}, {dt:.1f} s; per-sample throughput"}
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)

@@ -142,11 +142,15 @@ int32_t isokann_set_data_sharded(isokann_ctx *ctx, const float *xs, const float 
 /* Asynchronous form of isokann_set_data_sharded: ys_local, then xs, are streamed to the device on a second
  * CUDA stream.  The next Koopman pass (isokann_koopman / isokann_target / isokann_iterate) consumes ys chunk
  * by chunk as it arrives and the first reader of xs (isokann_chis, training, an N-D target) waits for xs on
- * the device, so the PCIe transfer overlaps the compute.  Both buffers should be page-locked and must stay
- * valid and unmodified until isokann_synchronize (or a call that returns results computed from them, such
- * as isokann_iterate) has returned. */
+ * the device, so the PCIe transfer overlaps the compute.  The library page-locks both buffers itself
+ * (cudaHostRegister; cached, so handing over the same arrays again costs nothing; buffers that are already
+ * page-locked are used as they are).  They must stay valid and unmodified until isokann_synchronize (or a call
+ * that returns results computed from them, such as isokann_iterate) has returned, and must not be freed while
+ * registered: call isokann_release_host_buffers first (isokann_destroy and a later isokann_set_data_async with
+ * other buffers release them too). */
 int32_t isokann_set_data_async(isokann_ctx *ctx, const float *xs, const float *ys_local, int64_t D, int64_t K,
                                int64_t N, int64_t n_offset, int64_t n_local);
+int32_t isokann_release_host_buffers(isokann_ctx *ctx);
 /* addcoords!(iso, coords) / mergedata (src/simulation.jl:162-185, src/iso.jl:238): append n_new start points and
  * their K Koopman samples to the resident data without re-uploading what is already there (single rank;
  * data must be library-owned).  The resident target becomes invalid, as in the reference where run! recomputes it. */
@@ -201,6 +205,17 @@ int32_t isokann_train_epoch(isokann_ctx *ctx, const int64_t *perm, int64_t minib
  * n_iter*epochs permutations of length N; losses_out receives n_iter*epochs values */
 int32_t isokann_iterate(isokann_ctx *ctx, int32_t transform, const isokann_target_opts *opts, int64_t n_iter,
                         int64_t epochs, int64_t minibatch, const int64_t *perms, double *losses_out);
+
+/* Diagnostics of the path's intermediates (loggers / parity tests):
+ *  - the flat gradient of the last optimiser step of train_epoch, i.e. what Zygote.withgradient returns at
+ *    src/iso.jl:185 (gradient of l/B, summed over ranks), in the flat parameter order;
+ *  - the d x d matrices of the last N-D isotarget: TransformPseudoInv's Kinv = chi*pinv(Kchi) (or K when
+ *    direct == 0) and T = schur(Kinv).vectors (src/isotarget.jl:165-168), both column-major Float32 as in Julia
+ *    (identity for ISA), and the final matrix A with target = A * Kchi after normalisation and fixperm
+ *    (row-major double; for TransformISA this is inv(X[i,:])' of src/isotarget.jl:93,104).  Any pointer may be NULL. */
+int32_t isokann_download_grads(isokann_ctx *ctx, float *flat, int64_t P);
+int32_t isokann_target_matrices(isokann_ctx *ctx, float *kinv_colmajor, float *schur_colmajor,
+                                double *applied_rowmajor);
 
 int32_t isokann_enable_timing(isokann_ctx *ctx, int32_t on);
 int32_t isokann_get_stats(isokann_ctx *ctx, isokann_stats *out);

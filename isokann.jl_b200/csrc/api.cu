@@ -592,6 +592,7 @@ void finish_nd_target(Ctx &c, Mat8 mat, bool normalize, bool permute) {
       for (int k = 0; k < d; ++k) m2.m[b * d + k] = mat.m[p[b] * d + k];
     mat = m2;
   }
+  for (int i = 0; i < d * d; ++i) c.last_mat[i] = mat.m[i];
   launch_apply(c, 2, c.kchi.p, nullptr, c.N, d, mat, c.target.p, c.red_d.p, &nb);
   double *part = read_back(c, c.red_d.p, (size_t)nb * d * 2);
   double mom[2 * kMaxD];
@@ -738,8 +739,13 @@ void target_pinv(Ctx &c, const isokann_target_opts &o) {
   for (int a = 0; a < d; ++a)
     for (int b = 0; b < d; ++b) Kf_col[a + b * d] = (float)Kmat[a * d + b];
   double T[kMaxD * kMaxD];
+  for (int i = 0; i < d * d; ++i) {
+    c.last_kinv[i] = Kf_col[i];
+    c.last_schur[i] = (i % (d + 1) == 0) ? 1.f : 0.f;
+  }
   if (o.eigenvecs) {
     IK_REQUIRE(host_schur_f32(Kf_col, d, Zf_col, nullptr), ISOKANN_DOMAIN_PINV, msg);
+    for (int i = 0; i < d * d; ++i) c.last_schur[i] = Zf_col[i];
     for (int a = 0; a < d; ++a)
       for (int b = 0; b < d; ++b) T[a * d + b] = (double)Zf_col[a + b * d];
   } else {
@@ -909,6 +915,15 @@ double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool par
   IK_REQUIRE(perm_host != nullptr, ISOKANN_BAD_ARGUMENT, "perm must not be NULL");
   IK_REQUIRE(minibatch >= 0, ISOKANN_BAD_ARGUMENT, "minibatch must be >= 0");
   const int64_t N = c.N;
+  {  // the indices feed device gathers (coords + idx*D, target[idx]): reject anything outside 1..N before the upload
+    int64_t lo = INT64_MAX, hi = INT64_MIN;
+    for (int64_t i = 0; i < N; ++i) {
+      lo = std::min(lo, perm_host[i]);
+      hi = std::max(hi, perm_host[i]);
+    }
+    IK_REQUIRE(lo >= 1 && hi <= N, ISOKANN_BAD_ARGUMENT,
+               "perm must hold 1-based indices in 1..N (got " + std::to_string(lo) + ".." + std::to_string(hi) + ")");
+  }
   const int64_t bs = (minibatch == 0 || N < minibatch) ? N : minibatch;  // src/iso.jl:180
   const int64_t nb = partial ? (N + bs - 1) / bs : N / bs;               // partial=false drops the tail
   c.timer.begin(KC_PHASE_TRAIN, c.stream);
@@ -952,6 +967,39 @@ void upload_rows(Ctx &c, const void *host, bool f64, int64_t count, float *dev) 
   }
 }
 
+// Page-lock caller memory for the asynchronous upload (cudaHostRegister) so that the DMA engine reads it directly
+// and the copy really overlaps the Koopman pass.  Registrations are cached per (pointer, size): a caller that hands
+// over the same arrays every iteration (Julia's iso.data) pays the pinning once.  Memory that is already page-locked
+// (cudaMallocHost, torch pin_memory) is left alone; if pinning fails the copy still works, staged by the driver.
+void release_host_registrations(Ctx &c) {
+  for (auto &r : c.host_regs)
+    if (r.ours) cudaHostUnregister(r.ptr);
+  c.host_regs.clear();
+  cudaGetLastError();
+}
+
+void ensure_host_registered(Ctx &c, int slot, const void *ptr, size_t bytes) {
+  if ((int)c.host_regs.size() <= slot) c.host_regs.resize(slot + 1);
+  Ctx::HostReg &r = c.host_regs[slot];
+  if (r.ptr == ptr && r.bytes >= bytes) return;
+  if (r.ours) cudaHostUnregister(r.ptr);
+  r = Ctx::HostReg{};
+  cudaGetLastError();
+  if (!ptr || bytes == 0) return;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) {
+    r.ptr = const_cast<void *>(ptr);  // already page-locked (or managed) by its owner
+    r.bytes = bytes;
+    return;
+  }
+  cudaGetLastError();
+  const cudaError_t e = cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault);
+  r.ptr = const_cast<void *>(ptr);
+  r.bytes = bytes;
+  r.ours = e == cudaSuccess;
+  if (e != cudaSuccess) cudaGetLastError();
+}
+
 void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_ptrs, int64_t D, int64_t K, int64_t N,
                    int64_t n_off, int64_t n_loc, bool async_ys = false) {
   if (c.ys_chunk_pts > 0 || c.xs_pending) {  // a previous asynchronous upload may still be running
@@ -985,6 +1033,8 @@ void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_pt
         // stream ys in on a second stream, ~64 MiB per chunk, one event per chunk; the Koopman pass waits per
         // chunk, so the PCIe transfer overlaps the forward pass over the chunks that already arrived
         if (!c.copy_stream) IK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        ensure_host_registered(c, 0, ys, (size_t)n_loc * K * D * sizeof(float));
+        ensure_host_registered(c, 1, xs, (size_t)N * D * sizeof(float));
         const int64_t pts = std::max<int64_t>(1, (64ll << 20) / (K * D * 4));
         const int64_t nchunks = (n_loc + pts - 1) / pts;
         while ((int64_t)c.ys_events.size() < nchunks) {
@@ -1259,6 +1309,7 @@ int32_t isokann_destroy(isokann_ctx *c) {
   }
   for (auto e : c->ys_events) cudaEventDestroy(e);
   if (c->xs_event) cudaEventDestroy(c->xs_event);
+  release_host_registrations(*c);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1670,6 +1721,26 @@ int32_t isokann_iterate(isokann_ctx *c, int32_t transform, const isokann_target_
   });
 }
 
+int32_t isokann_download_grads(isokann_ctx *c, float *flat, int64_t P) {
+  return guarded(c, [&] {
+    IK_REQUIRE(flat && P == c->P, ISOKANN_BAD_ARGUMENT, "parameter count mismatch");
+    IK_CUDA(cudaMemcpyAsync(flat, c->grads.p, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    sync_stream(*c);
+  });
+}
+
+int32_t isokann_target_matrices(isokann_ctx *c, float *kinv_colmajor, float *schur_colmajor, double *applied_rowmajor) {
+  return guarded(c, [&] {
+    IK_REQUIRE(c->d > 1 && c->has_target, ISOKANN_ERR_STATE, "no N-D target has been computed");
+    const int n = c->d * c->d;
+    for (int i = 0; i < n; ++i) {
+      if (kinv_colmajor) kinv_colmajor[i] = c->last_kinv[i];
+      if (schur_colmajor) schur_colmajor[i] = c->last_schur[i];
+      if (applied_rowmajor) applied_rowmajor[i] = c->last_mat[i];
+    }
+  });
+}
+
 int32_t isokann_enable_timing(isokann_ctx *c, int32_t on) {
   return guarded(c, [&] {
     c->timer.flush(c->stream);
@@ -1711,6 +1782,15 @@ int32_t isokann_synchronize(isokann_ctx *c) {
 }
 
 void *isokann_stream(isokann_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int32_t isokann_release_host_buffers(isokann_ctx *c) {
+  return guarded(c, [&] {
+    if (c->copy_stream) IK_CUDA(cudaStreamSynchronize(c->copy_stream));
+    c->xs_pending = false;
+    sync_stream(*c);
+    release_host_registrations(*c);
+  });
+}
 
 int32_t isokann_host_schur(const float *a_colmajor, int32_t d, float *z_colmajor, float *t_colmajor) {
   if (!a_colmajor || !z_colmajor || d < 1 || d > kMaxD) return ISOKANN_BAD_ARGUMENT;

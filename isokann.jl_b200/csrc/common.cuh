@@ -225,10 +225,21 @@ struct Ctx {
     return true;
   }
   bool xs_pending = false;
+  // caller buffers page-locked by isokann_set_data_async (slot 0: ys, 1: xs); ours = registered here
+  struct HostReg {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    bool ours = false;
+  };
+  std::vector<HostReg> host_regs;
   DevBuf<float> xs_stage;          // send buffer of the padded xs all-gather (unequal shards)
   bool xs_gather_pending = false;  // multi-rank async upload: only this rank's rows of xs came from the host
   DevBuf<float> chi_x, kchi, kchi_loc, gather_pad, target, w_loss;
   bool has_target = false;
+  // d x d matrices of the last N-D target (isokann_target_matrices): Kinv / K and its real Schur vectors
+  // (TransformPseudoInv, column-major like the reference's Julia matrices) and the final matrix applied to Kchi
+  float last_kinv[kMaxD * kMaxD] = {0}, last_schur[kMaxD * kMaxD] = {0};
+  double last_mat[kMaxD * kMaxD] = {0};
 
   // workspaces
   std::vector<DevBuf<float>> act;  // act[l]: rows x widths[l]

@@ -139,7 +139,7 @@ class Engine:
         self.N, self.K = N, K
 
     def set_data_async(self, xs, ys, n_offset: int = 0, n_local: Optional[int] = None):
-        """like set_data, but ys and then xs (float32, Fortran-ordered, ideally page-locked) are streamed in
+        """like set_data, but ys and then xs (float32, Fortran-ordered; page-locked by the library) are streamed in
         behind the call: the next Koopman pass consumes ys chunk-wise, the first reader of xs waits for it on
         the device; the caller keeps both alive until results computed from them have come back"""
         xs = julia_f32(xs, 2)
@@ -150,6 +150,11 @@ class Engine:
         self._keep = [xs, ys]
         self._check(self.lib.isokann_set_data_async(self.h, L.ptr(xs), L.ptr(ys), D, K, N, n_offset, n_local))
         self.N, self.K = N, K
+
+    def release_host_buffers(self):
+        """un-pin the arrays handed to set_data_async (call before freeing them)"""
+        self._check(self.lib.isokann_release_host_buffers(self.h))
+        self._keep = []
 
     def append_data(self, xs_new, ys_new):
         xs_new = julia_f32(xs_new, 2)
@@ -189,6 +194,21 @@ class Engine:
         out = np.empty(self.P, dtype=np.float32)
         self._check(self.lib.isokann_download_params(self.h, L.ptr(out), out.size))
         return out
+
+    def download_grads(self) -> np.ndarray:
+        """flat gradient of the last optimiser step (what Zygote.withgradient returns at src/iso.jl:185)"""
+        out = np.empty(self.P, dtype=np.float32)
+        self._check(self.lib.isokann_download_grads(self.h, L.ptr(out), out.size))
+        return out
+
+    def target_matrices(self):
+        """(Kinv, schur(Kinv).vectors, A) of the last N-D target; Julia-shaped (d, d) arrays, target = A @ Kchi"""
+        d = self.d
+        kinv = np.zeros((d, d), dtype=np.float32, order="F")
+        z = np.zeros((d, d), dtype=np.float32, order="F")
+        a = np.zeros((d, d), dtype=np.float64)
+        self._check(self.lib.isokann_target_matrices(self.h, L.ptr(kinv), L.ptr(z), L.ptr(a)))
+        return kinv, z, a
 
     def upload_opt_state(self, m, v=None, beta_t=None):
         m = np.ascontiguousarray(m, dtype=np.float32)

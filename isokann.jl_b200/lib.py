@@ -83,6 +83,7 @@ SIGNATURES = {
     "isokann_set_data_f64": (C.c_int32, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64]),
     "isokann_set_data_sharded": (C.c_int32, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "isokann_set_data_async": (C.c_int32, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "isokann_release_host_buffers": (C.c_int32, [_p]),
     "isokann_append_data": (C.c_int32, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64]),
     "isokann_keep_last": (C.c_int32, [_p, C.c_int64]),
     "isokann_chis_prop": (C.c_int32, [_p, _p]),
@@ -101,6 +102,8 @@ SIGNATURES = {
     "isokann_set_target": (C.c_int32, [_p, _p, C.c_int64, C.c_int64]),
     "isokann_train_epoch": (C.c_int32, [_p, _p, C.c_int64, C.c_int32, _d]),
     "isokann_iterate": (C.c_int32, [_p, C.c_int32, C.POINTER(TargetOpts), C.c_int64, C.c_int64, C.c_int64, _p, _d]),
+    "isokann_download_grads": (C.c_int32, [_p, _p, C.c_int64]),
+    "isokann_target_matrices": (C.c_int32, [_p, _p, _p, _p]),
     "isokann_enable_timing": (C.c_int32, [_p, C.c_int32]),
     "isokann_get_stats": (C.c_int32, [_p, C.POINTER(Stats)]),
     "isokann_reset_stats": (C.c_int32, [_p]),

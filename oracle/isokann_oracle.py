@@ -28,7 +28,7 @@ __all__ = [
     "flatten_params", "unflatten_params", "num_params", "layernorm", "sigmoid",
     "forward", "forward_cache", "expectation", "shiftscale", "DomainError",
     "indexmap", "myisa", "fixperm", "isotarget_shiftscale", "isotarget_isa",
-    "isotarget_pinv", "isotarget", "OptConfig", "OptState", "opt_init",
+    "isotarget_pinv", "isotarget", "isa_from_chi", "pinv_from_chi", "OptConfig", "OptState", "opt_init",
     "opt_update", "loss_weights", "batch_loss_and_grad", "train_batch",
     "run", "weighted_expectation", "chi_vjp",
 ]
@@ -67,9 +67,48 @@ def pair_table(n_atoms: int, cols: Optional[Sequence[int]] = None) -> np.ndarray
     return np.array([(cols[i - 1] - 1, cols[j - 1] - 1) for i, j in h], dtype=np.int32).reshape(-1, 2)
 
 
-def _dists_from_pairs(x: np.ndarray, pairs0: np.ndarray, out_dtype) -> np.ndarray:
+_CLIB = None
+
+
+def _clib():
+    """oracle/liboracle.so (oracle/isokann_oracle.c, built by oracle/build.py): the same featurizer
+    arithmetic in C, used for inputs too large for the numpy gathers; None if it has not been built."""
+    global _CLIB
+    if _CLIB is None:
+        import ctypes
+        from pathlib import Path
+        p = Path(__file__).resolve().parent / "liboracle.so"
+        _CLIB = ctypes.CDLL(str(p)) if p.exists() else False
+    return _CLIB or None
+
+
+def _dists_from_pairs_c(x: np.ndarray, pairs0: np.ndarray, out_dtype) -> Optional[np.ndarray]:
+    import ctypes
+    lib = _clib()
+    if lib is None or x.dtype not in (F32, F64) or np.dtype(out_dtype) not in (np.dtype(F32), np.dtype(F64)):
+        return None
+    d = x.shape[-1]
+    xc = np.ascontiguousarray(x).reshape(-1, d)
+    p0 = np.ascontiguousarray(pairs0, dtype=np.int32).reshape(-1, 2)
+    out = np.empty((xc.shape[0], p0.shape[0]), dtype=out_dtype)
+    fn = getattr(lib, "oracle_pdists_%s_%s" % ("f32" if xc.dtype == F32 else "f64",
+                                               "f32" if out.dtype == F32 else "f64"))
+    fn.restype = None
+    fn(ctypes.c_void_p(xc.ctypes.data), ctypes.c_int64(xc.shape[0]), ctypes.c_int64(d),
+       ctypes.c_void_p(p0.ctypes.data), ctypes.c_int(p0.shape[0]), ctypes.c_void_p(out.ctypes.data))
+    return out.reshape(*x.shape[:-1], p0.shape[0])
+
+
+def _dists_from_pairs(x: np.ndarray, pairs0: np.ndarray, out_dtype, use_c: Optional[bool] = None) -> np.ndarray:
     d = x.shape[-1]
     lead = x.shape[:-1]
+    x = np.asarray(x)
+    if use_c is None:
+        use_c = x.size >= (1 << 16)
+    if use_c:
+        r = _dists_from_pairs_c(x, pairs0, out_dtype)
+        if r is not None:
+            return r
     c = np.asarray(x, dtype=F64).reshape(-1, d // 3, 3)
     out = np.empty((c.shape[0], len(pairs0)), dtype=out_dtype)
     step = max(1, (1 << 22) // max(1, len(pairs0)))
@@ -391,28 +430,30 @@ def isotarget_shiftscale(m: Model, xsf: np.ndarray, ysf: np.ndarray) -> np.ndarr
     return shiftscale(expectation(m, ysf))
 
 
-def isotarget_isa(m: Model, xsf: np.ndarray, ysf: np.ndarray, permute: bool = True,
-                  whitening: bool = False) -> np.ndarray:
-    """src/isotarget.jl:100-107.  Returns (N, d) float32."""
-    chi = forward(m, xsf)
+def isa_from_chi(chi: np.ndarray, ks: np.ndarray, permute: bool = True, whitening: bool = False) -> np.ndarray:
+    """body of src/isotarget.jl:100-107 given chi = model(xs) and ks = expectation(model, ys), both (N, d)."""
     assert chi.shape[1] > 1, "TransformISA does not work with one dimensional chi functions"
-    ks = expectation(m, ysf)                              # (N, d) float32
     A = myisa(ks, whitening)                              # (d, d) float64 = inv(X[i,:])
     # Julia: target = A' * ks  ([d,d] x [d,N]); records layout: ks_rec @ A
     target = ks.astype(F64) @ A
     if permute:
         target = fixperm(target, chi)
-    return target.astype(xsf.dtype)
+    return target.astype(chi.dtype)
 
 
-def isotarget_pinv(m: Model, xsf: np.ndarray, ysf: np.ndarray, normalize: bool = True,
-                   direct: bool = True, eigenvecs: bool = True, permute: bool = True) -> np.ndarray:
-    """src/isotarget.jl:152-179 (float32 LAPACK via scipy: pinv = gesdd SVD with
-    rtol = eps*min(d,N); schur = sgees, unsorted).  Returns (N, d) float32."""
+def isotarget_isa(m: Model, xsf: np.ndarray, ysf: np.ndarray, permute: bool = True,
+                  whitening: bool = False) -> np.ndarray:
+    """src/isotarget.jl:100-107.  Returns (N, d) float32."""
+    return isa_from_chi(forward(m, xsf), expectation(m, ysf), permute, whitening).astype(xsf.dtype)
+
+
+def pinv_from_chi(chi_r: np.ndarray, kchi_r: np.ndarray, normalize: bool = True, direct: bool = True,
+                  eigenvecs: bool = True, permute: bool = True, details: Optional[dict] = None) -> np.ndarray:
+    """body of src/isotarget.jl:152-179 given chi = model(xs) and kchi = expectation(model, ys), both (N, d)
+    (float32 LAPACK via scipy: pinv = gesdd SVD with rtol = eps*min(d,N); schur = sgees, unsorted).
+    ``details`` receives Kinv (or K) and the Schur vectors T, Julia-shaped (d, d)."""
     import scipy.linalg as sla
-    chi_r = forward(m, xsf)
     assert chi_r.shape[1] > 1, "TransformPseudoInv does not work with one dimensional chi functions"
-    kchi_r = expectation(m, ysf)
     chi = np.ascontiguousarray(chi_r.T)                   # Julia-shaped [d, N]
     kchi = np.ascontiguousarray(kchi_r.T)
     d, n = kchi.shape
@@ -427,9 +468,12 @@ def isotarget_pinv(m: Model, xsf: np.ndarray, ysf: np.ndarray, normalize: bool =
         T = sla.schur(Kinv, output="real")[1] if eigenvecs else np.eye(d, dtype=kchi.dtype)
         target = (T @ Kinv) @ kchi
     else:
-        K = kchi @ kchi_inv
-        T = sla.schur(K, output="real")[1] if eigenvecs else np.eye(d, dtype=kchi.dtype)
-        target = (T @ np.linalg.inv(K)) @ kchi
+        Kinv = kchi @ kchi_inv
+        T = sla.schur(Kinv, output="real")[1] if eigenvecs else np.eye(d, dtype=kchi.dtype)
+        target = (T @ np.linalg.inv(Kinv)) @ kchi
+    if details is not None:
+        details["Kinv"] = Kinv
+        details["T"] = T
     target = target.astype(kchi.dtype)
     if normalize:
         l1 = np.abs(target).sum(axis=1, keepdims=True, dtype=kchi.dtype)
@@ -437,7 +481,13 @@ def isotarget_pinv(m: Model, xsf: np.ndarray, ysf: np.ndarray, normalize: bool =
     t_r = np.ascontiguousarray(target.T)
     if permute:
         t_r = fixperm(t_r, chi_r)
-    return t_r.astype(xsf.dtype)
+    return t_r.astype(chi_r.dtype)
+
+
+def isotarget_pinv(m: Model, xsf: np.ndarray, ysf: np.ndarray, normalize: bool = True,
+                   direct: bool = True, eigenvecs: bool = True, permute: bool = True) -> np.ndarray:
+    """src/isotarget.jl:152-179.  Returns (N, d) float32."""
+    return pinv_from_chi(forward(m, xsf), expectation(m, ysf), normalize, direct, eigenvecs, permute).astype(xsf.dtype)
 
 
 def isotarget(kind: str, m: Model, xsf: np.ndarray, ysf: np.ndarray, **kw) -> np.ndarray:
