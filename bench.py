@@ -145,8 +145,15 @@ def run_reference(args, pkg):
     B = args.minibatch if args.minibatch is not None else w.minibatch
     target = args.target or w.target
     Ns = cpu_sample_size(w, N, K, args.cpu_sample)
-    Bs = min(B, Ns) if B else 0
     steps, warm = max(1, args.steps), max(0, args.warmup)
+    if args.cpu_sample <= 0 and Ns >= 4096:
+        # keep the whole --steps/--warmup run within ~4 minutes: calibrate on a 1/8 sample of the sample and halve
+        # Ns (1/64 -> 1/128 -> ...) while the projected run time exceeds the budget
+        n0 = max(256, Ns // 8)
+        _, dt0 = cpu_iteration_sample(pkg, w, n0, K, min(B, n0) if B else 0, 1, 1, target)
+        while Ns > 1024 and dt0 * (Ns / n0) * (steps + warm) > 240.0:
+            Ns //= 2
+    Bs = min(B, Ns) if B else 0
     val, dt = cpu_iteration_sample(pkg, w, Ns, K, Bs, steps, warm, target)
     threads = blas_threads()
     sample = (f"{Ns} of {N} start points (x{K} Koopman samples) = 1/{N / Ns:.0f} of the workload, one full iteration "

@@ -129,13 +129,20 @@ def test_c5_shaped_optimiser_step(pkg, oracle):
             assert np.abs(flat1 - ref1).max() < 1.9e-3 * 5e-3 * np.abs(g_ref).max() + 1e-7
         else:                   # Adam's first step is eta*g'/(|g'|+eps): compare where the sign of g' is settled
             gp = g_ref + np.float32(1e-4) * flat0
-            e_abs = np.abs(g_lib - g_ref).max()
-            settled = np.abs(gp) > 100 * e_abs + 1e-7                   # d(step) ~ eta * e_abs / |g'| there
-            errs["adam.params_settled"] = np.abs(flat1 - ref1)[settled].max()
-            errs["adam.settled_fraction"] = settled.mean()
-            assert settled.mean() > 0.9, (settled.mean(), e_abs)
-            assert np.abs(flat1 - ref1)[settled].max() < 2e-5
-            assert np.abs(flat1 - ref1).max() <= 2.0e-3 + 1e-6            # never more than one full step apart
+            dpar = np.abs(flat1 - ref1)
+            frac, worst = [], 0.0
+            for name, sl in blocks:
+                e_abs = np.abs(g_lib[sl] - g_ref[sl]).max()
+                settled = np.abs(gp[sl]) > 100 * e_abs + 1e-9               # d(step) ~ eta * e_abs / |g'| there
+                frac.append(settled.mean())
+                if settled.any():
+                    worst = max(worst, dpar[sl][settled].max())
+            errs["adam.params_settled"] = worst
+            errs["adam.settled_fraction_min"] = min(frac)
+            note("c5_step", **errs)
+            assert min(frac) > 0.5, frac
+            assert worst < 2e-5
+            assert dpar.max() <= 2.0e-3 + 1e-6                              # never more than one full step apart
         chi1 = records(pkg.chis(iso))
         m1 = oracle.unflatten_params(om.copy(), ref1)
         rows = np.arange(0, N, 16)
