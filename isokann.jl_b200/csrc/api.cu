@@ -309,10 +309,15 @@ void tc_ensure_delta(Ctx &c, int64_t Bloc) {
   t.dlast.ensure(Bloc, 64);
 }
 
+void comm_bucket_upper(Ctx &c);
+
 // head_done: launch_thin_head already produced delta_L (split, t.dlast) and delta_{L-1} (t.delta[0])
-void backward_tc(Ctx &c, int64_t Bloc, bool head_done) {
+// overlap: multi-rank step -- the gradients of layers >= 2 go to the communication stream as soon as the weight
+//          gradient of layer 2 has been launched (comm_bucket_upper)
+void backward_tc(Ctx &c, int64_t Bloc, bool head_done, bool overlap = false) {
   TcState &t = *c.tcs;
   const int L = c.L, d = c.d;
+  const int sms = c.num_sms - c.sm_reserve;
   tc_ensure_delta(c, Bloc);
   int cur = 0;
   {  // last (thin) layer
@@ -327,7 +332,7 @@ void backward_tc(Ctx &c, int64_t Bloc, bool head_done) {
     w.epi = TC_EPI_F32; w.act = ISOKANN_ACT_IDENTITY;
     w.ldc = d;
     const int tiles = cdiv(w.M, 128);
-    const int splits = std::max(1, std::min(c.num_sms / tiles, (int)(Bloc / 1024)));
+    const int splits = std::max(1, std::min(sms / tiles, (int)(Bloc / 1024)));
     if (splits > 1) {
       c.splitk.ensure((size_t)splits * w.M * w.N);
       w.out_f32 = c.splitk.p;
@@ -339,6 +344,7 @@ void backward_tc(Ctx &c, int64_t Bloc, bool head_done) {
       w.splits = 1;
       launch_tc_gemm(c, w);
     }
+    if (overlap && l == 1) comm_bucket_upper(c);
     if (!head_done)
       launch_thin_dgrad(c, c.delta_a.p, Bloc, d, c.params.p + c.off_w[l], fin, t.act[l].hi.p, t.act[l].lo.p, t.wp[l],
                         c.cfg.activation, t.delta[cur].hi.p, t.delta[cur].lo.p, t.wp[l]);
@@ -357,7 +363,7 @@ void backward_tc(Ctx &c, int64_t Bloc, bool head_done) {
     w.ldc = fout;
     const int tiles = cdiv(w.M, 128) * cdiv(w.N, 256);
     // as many split-K slices as fit in ONE wave of CTAs (a partial second wave would double the kernel time)
-    int splits = std::max(1, std::min(c.num_sms / tiles, (int)(Bloc / 2048)));
+    int splits = std::max(1, std::min(sms / tiles, (int)(Bloc / 2048)));
     if (splits > 1) {
       c.splitk.ensure((size_t)splits * w.M * w.N);
       w.out_f32 = c.splitk.p;
@@ -369,6 +375,7 @@ void backward_tc(Ctx &c, int64_t Bloc, bool head_done) {
       w.splits = 1;
       launch_tc_gemm(c, w);
     }
+    if (overlap && l == 1 && l < L - 1) comm_bucket_upper(c);
     if (l > 0) {
       // delta_l = (delta_{l+1} * W_l^T) .* act'(z_l)
       TcGemm g{};
@@ -804,12 +811,36 @@ int pick_splits(const Ctx &c, int Mout, int Nout, int Kred) {
   return std::min(s, 64);
 }
 
+// launch on another stream through the same wrappers; the context's stream is restored even if a launch throws
+struct StreamScope {
+  Ctx &c;
+  cudaStream_t saved;
+  StreamScope(Ctx &ctx, cudaStream_t s) : c(ctx), saved(ctx.stream) { c.stream = s; }
+  ~StreamScope() { c.stream = saved; }
+};
+
+// in-place all-reduce(SUM) of grads[lo, hi) on the context's current stream
+void allreduce_grads(Ctx &c, int64_t lo, int64_t hi) {
+  std::string err;
+  c.timer.begin(KC_NCCL, c.stream);
+  int rc = nccl_allreduce_sum_f32(c.nccl, c.comm, c.grads.p + lo, (size_t)(hi - lo), c.stream, err);
+  c.timer.end(c.stream);
+  IK_REQUIRE(rc == ISOKANN_OK, ISOKANN_ERR_NCCL, err);
+  c.stats.nccl_calls++;
+}
+
+void train_step_overlapped(Ctx &c, int64_t s0, int64_t Bloc, int64_t len);
+
 // one optimiser step on the minibatch perm[start, start+len): forward, loss, backward, update
 void train_step(Ctx &c, int64_t start, int64_t len) {
   int64_t loff, Bloc;
   split_range(len, c.world, c.rank, &loff, &Bloc);
   const int64_t s0 = start + loff;
   const int L = c.L, d = c.d;
+  if (c.comm_overlap) {  // multi-rank tensor-core path: bucketed gradient exchange next to the backward pass
+    train_step_overlapped(c, s0, Bloc, len);
+    return;
+  }
   if (Bloc == 0) {
     IK_CUDA(cudaMemsetAsync(c.grads.p, 0, (size_t)(c.P + 4) * sizeof(float), c.stream));
   } else if (c.fused_train && Bloc <= 8192) {
@@ -891,21 +922,133 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
                        c.cfg.widths[1], c.grads.p + c.off_gamma, c.grads.p + c.off_beta, c.grads.p + c.off_w[0],
                        c.grads.p + c.off_b[0]);
   }
-  if (c.world > 1) {
-    std::string err;
-    c.timer.begin(KC_NCCL, c.stream);
-    int rc = nccl_allreduce_sum_f32(c.nccl, c.comm, c.grads.p, (size_t)c.P + 2, c.stream, err);
-    c.timer.end(c.stream);
-    IK_REQUIRE(rc == ISOKANN_OK, ISOKANN_ERR_NCCL, err);
-    c.stats.nccl_calls++;
-  }
-  launch_optimiser(c, c.P, c.beta_t[0], c.beta_t[1]);
-  if (c.cfg.optimiser == ISOKANN_OPT_ADAM) {
-    c.beta_t[0] *= c.cfg.beta1;
-    c.beta_t[1] *= c.cfg.beta2;
-  }
+  if (c.world > 1) allreduce_grads(c, 0, c.P + 2);
+  launch_optimiser(c, c.P);
   c.folded_valid = false;
   c.tc_weights_valid = false;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-rank training step on the tensor-core path.  The flat gradient is exchanged in two buckets on a second
+// stream while the backward pass is still running:
+//   upper bucket  [off_w[1], P+2): layers >= 2 and the packed step loss -- complete once the weight gradient of
+//                 layer 2 has run; all-reduce -> optimiser -> split-bf16 operands of those layers, all next to the
+//                 data-gradient GEMM of layer 2 and the weight-gradient GEMM of layer 1 on the main stream
+//   lower bucket  [0, off_w[1]): LayerNorm affine + layer 1 -- after unfold_ln; all-reduce -> optimiser -> fold ->
+//                 operands of layer 1, next to the gather + featurizer of the NEXT minibatch
+// The refreshed operands go to a second set of buffers (the data-gradient GEMM still reads the current set) and the
+// two sets are swapped at the end of the step.  The GEMMs of the step leave `sm_reserve` SMs to the NCCL kernels: a
+// persistent GEMM CTA fills an SM's shared memory, so without the reserve the collective would only start when a
+// GEMM ends.  Same arithmetic as the single-stream step (same global minibatch, gradient of l/B, src/iso.jl:184-192).
+// ------------------------------------------------------------------------------------------
+void join_comm_stream(Ctx &c);
+
+void ensure_comm_stream(Ctx &c) {
+  if (c.comm_stream) return;
+  IK_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+  IK_CUDA(cudaEventCreateWithFlags(&c.ev_upper, cudaEventDisableTiming));
+  IK_CUDA(cudaEventCreateWithFlags(&c.ev_lower, cudaEventDisableTiming));
+  IK_CUDA(cudaEventCreateWithFlags(&c.ev_weights, cudaEventDisableTiming));
+}
+
+void prep_layer_alt(Ctx &c, int l) {
+  TcState &t = *c.tcs;
+  const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
+  launch_prep_weights(c, layer_segment(c, l), fin, fout, t.wF_alt[l].hi.p, t.wF_alt[l].lo.p, t.wp[l],
+                      l > 0 ? t.wD_alt[l].hi.p : nullptr, l > 0 ? t.wD_alt[l].lo.p : nullptr, l > 0 ? t.wp[l + 1] : 0);
+}
+
+void comm_bucket_upper(Ctx &c) {
+  IK_CUDA(cudaEventRecord(c.ev_upper, c.stream));
+  StreamScope on(c, c.comm_stream);
+  IK_CUDA(cudaStreamWaitEvent(c.stream, c.ev_upper, 0));
+  const int64_t lo = c.off_w[1];
+  allreduce_grads(c, lo, c.P + 2);
+  launch_optimiser_range(c, lo, c.P, true);
+  for (int l = 1; l + 1 < c.L; ++l) prep_layer_alt(c, l);
+}
+
+void comm_bucket_lower(Ctx &c) {
+  IK_CUDA(cudaEventRecord(c.ev_lower, c.stream));
+  StreamScope on(c, c.comm_stream);
+  IK_CUDA(cudaStreamWaitEvent(c.stream, c.ev_lower, 0));
+  allreduce_grads(c, 0, c.off_w[1]);
+  launch_optimiser_range(c, 0, c.off_w[1], false);
+  launch_advance_beta(c);
+  if (c.ln)
+    launch_fold_ln(c, c.params.p + c.off_gamma, c.params.p + c.off_beta, c.params.p + c.off_w[0],
+                   c.params.p + c.off_b[0], c.F, c.cfg.widths[1], c.folded1.p);
+  prep_layer_alt(c, 0);
+  IK_CUDA(cudaEventRecord(c.ev_weights, c.stream));
+}
+
+void train_step_overlapped(Ctx &c, int64_t s0, int64_t Bloc, int64_t len) {
+  TcState &t = *c.tcs;
+  const int L = c.L;
+  ensure_comm_stream(c);
+  tc_ensure_rows(c, Bloc);
+  if (!c.weights_in_flight) ensure_tc_weights(c);
+  for (int l = 0; l + 1 < L; ++l) {  // second operand set
+    t.wF_alt[l].ensure(c.cfg.widths[l + 1], t.wp[l]);
+    if (l > 0) t.wD_alt[l].ensure(c.cfg.widths[l], t.wp[l + 1]);
+  }
+  if (Bloc == 0) {  // a ragged last minibatch can leave this rank without rows: it contributes zeros
+    join_comm_stream(c);
+    IK_CUDA(cudaMemsetAsync(c.grads.p, 0, (size_t)(c.P + 4) * sizeof(float), c.stream));
+    comm_bucket_upper(c);
+    comm_bucket_lower(c);
+    std::swap(t.wF, t.wF_alt);
+    std::swap(t.wD, t.wD_alt);
+    c.weights_in_flight = c.folded_valid = c.tc_weights_valid = true;
+    return;
+  }
+  const bool pairs = c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
+  // gather + featurizer of this minibatch: independent of the weights, so it runs beside the tail of the previous step
+  launch_featurize_split(c, c.xs, c.perm_dev.p, s0, Bloc, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0]);
+  if (c.weights_in_flight) {
+    IK_CUDA(cudaStreamWaitEvent(c.stream, c.ev_weights, 0));
+    c.weights_in_flight = false;
+  }
+  const bool head = !c.tc_no_head && thin_head_eligible(c);
+  {
+    struct Reset {
+      bool &f;
+      ~Reset() { f = false; }
+    } reset{c.head_fused_now};
+    c.head_fused_now = head;
+    forward_rows_tc(c, nullptr, nullptr, 0, Bloc, true, true, &t.act[0]);
+  }
+  c.delta_a.ensure((size_t)Bloc * c.maxw);
+  const int last = L - 1;
+  tc_ensure_delta(c, Bloc);
+  if (head) {
+    c.red_d.ensure(1024);
+    launch_thin_head(c, t.act[last].hi.p, t.act[last].lo.p, Bloc, c.cfg.widths[last], t.wp[last],
+                     c.params.p + c.off_w[last], c.target.p, c.perm_dev.p + s0, c.w_loss.p, (double)len, c.act[L].p,
+                     c.delta_a.p, t.dlast.hi.p, t.dlast.lo.p, 64, t.delta[0].hi.p, t.delta[0].lo.p, t.wp[last],
+                     c.red_d.p, c.ticket.p, c.grads.p + c.P);
+  } else {
+    launch_loss_delta(c, c.act[L].p, c.target.p, c.perm_dev.p, s0, c.w_loss.p, Bloc, c.d, (double)len,
+                      c.cfg.last_activation, c.delta_a.p, c.red_d.p, c.ticket.p, c.grads.p + c.P);
+  }
+  backward_tc(c, Bloc, head, true);
+  if (c.ln)
+    launch_unfold_ln(c, c.params.p + c.off_gamma, c.params.p + c.off_beta, c.params.p + c.off_w[0], c.gfold.p, c.F,
+                     c.cfg.widths[1], c.grads.p + c.off_gamma, c.grads.p + c.off_beta, c.grads.p + c.off_w[0],
+                     c.grads.p + c.off_b[0]);
+  comm_bucket_lower(c);
+  std::swap(t.wF, t.wF_alt);
+  std::swap(t.wD, t.wD_alt);
+  c.weights_in_flight = true;   // the next reader of the parameters / operands waits for ev_weights
+  c.folded_valid = true;
+  c.tc_weights_valid = true;
+}
+
+// order the main stream behind the communication stream (end of an epoch, or before anything else reads the model)
+void join_comm_stream(Ctx &c) {
+  if (!c.weights_in_flight) return;
+  IK_CUDA(cudaStreamWaitEvent(c.stream, c.ev_weights, 0));
+  c.weights_in_flight = false;
 }
 
 double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool partial) {
@@ -932,9 +1075,23 @@ double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool par
   IK_CUDA(cudaMemcpyAsync(c.perm_raw.p, perm_host, (size_t)N * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
   launch_perm_to_zero_based(c, c.perm_raw.p, N, c.perm_dev.p);
   IK_CUDA(cudaMemsetAsync(c.epoch_loss.p, 0, sizeof(double), c.stream));
-  for (int64_t i = 0; i < nb; ++i) {
-    const int64_t start = i * bs;
-    train_step(c, start, std::min(bs, N - start));
+  {
+    // every rank gets rows in every step (bs >= world), so all ranks take the same code path
+    const bool overlap = c.world > 1 && c.tc && !c.tcn && c.L >= 2 && !c.no_comm_overlap && bs >= c.world;
+    struct Scope {
+      Ctx &c;
+      ~Scope() {
+        c.comm_overlap = false;
+        c.sm_reserve = 0;
+      }
+    } scope{c};
+    c.comm_overlap = overlap;
+    c.sm_reserve = overlap ? c.comm_sms : 0;
+    for (int64_t i = 0; i < nb; ++i) {
+      const int64_t start = i * bs;
+      train_step(c, start, std::min(bs, N - start));
+    }
+    join_comm_stream(c);
   }
   c.timer.end(c.stream);
   double *lp = read_back(c, c.epoch_loss.p, 1);
@@ -1232,11 +1389,16 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
       c->tcs->act.resize(c->L);
       c->tcs->wF.resize(c->L);
       c->tcs->wD.resize(c->L);
+      c->tcs->wF_alt.resize(c->L);
+      c->tcs->wD_alt.resize(c->L);
       // padded row length: room for a constant-1 column behind the activations (bias column of the wgrad GEMM)
       for (int l = 0; l <= c->L; ++l) c->tcs->wp.push_back((cfg->widths[l] + 1 + 63) & ~63);
     }
-    c->beta_t[0] = cfg->beta1;
-    c->beta_t[1] = cfg->beta2;
+    c->beta_dev.ensure(2);
+    {
+      const float bt[2] = {cfg->beta1, cfg->beta2};
+      IK_CUDA(cudaMemcpy(c->beta_dev.p, bt, sizeof(bt), cudaMemcpyHostToDevice));
+    }
     c->act.resize(c->L + 1);
     c->flags.ensure(1);
     c->ticket.ensure(1);
@@ -1276,6 +1438,8 @@ int32_t isokann_destroy(isokann_ctx *c) {
     for (auto &b : c->tcs->act) b.release();
     for (auto &b : c->tcs->wF) b.release();
     for (auto &b : c->tcs->wD) b.release();
+    for (auto &b : c->tcs->wF_alt) b.release();
+    for (auto &b : c->tcs->wD_alt) b.release();
     c->tcs->delta[0].release();
     c->tcs->delta[1].release();
     c->tcs->dot_partial.release();
@@ -1306,6 +1470,13 @@ int32_t isokann_destroy(isokann_ctx *c) {
   if (c->copy_stream) {
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamDestroy(c->copy_stream);
+  }
+  if (c->comm_stream) {
+    cudaStreamSynchronize(c->comm_stream);
+    cudaStreamDestroy(c->comm_stream);
+    cudaEventDestroy(c->ev_upper);
+    cudaEventDestroy(c->ev_lower);
+    cudaEventDestroy(c->ev_weights);
   }
   for (auto e : c->ys_events) cudaEventDestroy(e);
   if (c->xs_event) cudaEventDestroy(c->xs_event);
@@ -1343,6 +1514,12 @@ int32_t isokann_comm_init(isokann_ctx *c, int32_t world, int32_t rank, const voi
       return;
     }
     IK_REQUIRE(id128 != nullptr, ISOKANN_BAD_ARGUMENT, "id128 must not be NULL");
+    // the gradient all-reduces run beside the GEMMs of the backward pass: bound the SMs NCCL may take and leave
+    // exactly that many free (train_step_overlapped); a user setting of NCCL_MAX_CTAS is respected
+    c->no_comm_overlap = getenv("ISOKANN_NO_COMM_OVERLAP") != nullptr;
+    if (const char *e = getenv("ISOKANN_COMM_SMS")) c->comm_sms = std::max(0, std::min(64, atoi(e)));
+    if (!c->no_comm_overlap && c->comm_sms > 0) setenv("NCCL_MAX_CTAS", std::to_string(c->comm_sms).c_str(), 0);
+    if (const char *e = getenv("NCCL_MAX_CTAS")) c->comm_sms = std::max(0, std::min(64, atoi(e)));
     std::string err;
     c->nccl = nccl_load(err);
     IK_REQUIRE(c->nccl != nullptr, ISOKANN_ERR_NCCL, err);
@@ -1519,8 +1696,7 @@ int32_t isokann_upload_opt_state(isokann_ctx *c, const float *m, const float *v,
     if (c->cfg.optimiser == ISOKANN_OPT_ADAM) {
       IK_REQUIRE(v && beta_t, ISOKANN_BAD_ARGUMENT, "Adam state needs v and beta_t");
       IK_CUDA(cudaMemcpyAsync(c->opt_v.p, v, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-      c->beta_t[0] = beta_t[0];
-      c->beta_t[1] = beta_t[1];
+      IK_CUDA(cudaMemcpyAsync(c->beta_dev.p, beta_t, 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     }
     sync_stream(*c);
   });
@@ -1532,10 +1708,8 @@ int32_t isokann_download_opt_state(isokann_ctx *c, float *m, float *v, float *be
     IK_CUDA(cudaMemcpyAsync(m, c->opt_m.p, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (c->cfg.optimiser == ISOKANN_OPT_ADAM) {
       if (v) IK_CUDA(cudaMemcpyAsync(v, c->opt_v.p, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-      if (beta_t) {
-        beta_t[0] = c->beta_t[0];
-        beta_t[1] = c->beta_t[1];
-      }
+      if (beta_t)
+        IK_CUDA(cudaMemcpyAsync(beta_t, c->beta_dev.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     }
     sync_stream(*c);
   });

@@ -141,7 +141,9 @@ void launch_fold_ln(Ctx &c, const float *gamma, const float *beta, const float *
                     float *folded);
 void launch_unfold_ln(Ctx &c, const float *gamma, const float *beta, const float *W1, const float *gfold, int F,
                       int h1, float *g_gamma, float *g_beta, float *g_W1, float *g_b1);
-void launch_optimiser(Ctx &c, int64_t P, float bt1, float bt2);
+void launch_optimiser(Ctx &c, int64_t P);  // whole vector + beta^t advance
+void launch_optimiser_range(Ctx &c, int64_t lo, int64_t hi, bool accumulate_loss);
+void launch_advance_beta(Ctx &c);
 bool narrow_train_eligible(const isokann_config &g);
 bool tiny_forward_eligible(const isokann_config &g);
 void launch_tiny_forward(Ctx &c, const float *in, int64_t M, float *out);
@@ -183,7 +185,7 @@ struct Ctx {
 
   // parameters, gradients (+4 tail floats: packed step loss), optimiser state
   DevBuf<float> params, grads, opt_m, opt_v, folded1, gfold;
-  float beta_t[2] = {0.f, 0.f};
+  DevBuf<float> beta_dev;     // Adam: running (beta1^t, beta2^t), device-resident (replayable steps)
   bool folded_valid = false;  // folded1 matches the current parameters
   bool tc = false;            // wide Dense layers run on tcgen05 (3xBF16 split)
   bool tiny = false;          // every width <= 16, no featurizer/LayerNorm: thread-per-sample forward
@@ -257,6 +259,14 @@ struct Ctx {
   Nccl *nccl = nullptr;
   void *comm = nullptr;
   int world = 1, rank = 0;
+  // bucketed gradient exchange beside the backward pass (train_step_overlapped in api.cu)
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_upper = nullptr, ev_lower = nullptr, ev_weights = nullptr;
+  bool comm_overlap = false;      // set while train_epoch runs the overlapped step
+  bool no_comm_overlap = false;   // ISOKANN_NO_COMM_OVERLAP=1: single-stream step with one all-reduce (A/B)
+  bool weights_in_flight = false; // the communication stream still owes the refreshed parameters (ev_weights)
+  int comm_sms = 16;              // SMs the training-step GEMMs leave to NCCL (= NCCL_MAX_CTAS set at comm init)
+  int sm_reserve = 0;             // currently reserved (comm_sms during an overlapped epoch)
 
   // accounting
   isokann_stats stats{};

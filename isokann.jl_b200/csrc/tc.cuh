@@ -66,6 +66,7 @@ struct TcState {
   std::vector<SplitBuf> act;   // act[l], l = 0..L-1: row-major rows x wp_l
   std::vector<SplitBuf> wF;    // forward operand of layer l (l = 0..L-2): [w_{l+1} x wp_l]
   std::vector<SplitBuf> wD;    // dgrad operand of layer l   (l = 1..L-2): [w_l x wp_{l+1}]
+  std::vector<SplitBuf> wF_alt, wD_alt;  // second operand set: refreshed on the communication stream, then swapped in
   SplitBuf delta[2];           // row-major delta ping-pong
   SplitBuf x_alt;              // second x_hat buffer: the featurizer of chunk i+1 overlaps the GEMMs of chunk i
   cudaStream_t feat_stream = nullptr;

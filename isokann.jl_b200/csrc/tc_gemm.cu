@@ -833,8 +833,9 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   }
   // 2-CTA pairs for the large K-major GEMMs (forward / data gradient): B crosses L2 -> SMEM once per pair
   const int m_tiles2 = cdiv(g.M, 2 * BM);
+  const int sms = c.num_sms - c.sm_reserve;  // an overlapped multi-rank step leaves SMs to the NCCL kernels
   const bool pair = !g.mn_major && g.epi != TC_EPI_F32 && g.epi != TC_EPI_TAIL && g.N > BN / 2 &&
-                    m_tiles2 * p.n_tiles >= c.num_sms / 2 && !c.tc_no_pair;
+                    m_tiles2 * p.n_tiles >= sms / 2 && !c.tc_no_pair;
   if (pair) {
     if (c.attr_needed(Ctx::ATTR_TC2)) {
       IK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TC_EPI_BIAS_ACT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -843,7 +844,7 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
     }
     make_map(&mbh, g.b_hi, g.N, g.K, g.ldb, BN / 2);  // each CTA of the pair loads half of the B tile
     make_map(&mbl, g.b_lo, g.N, g.K, g.ldb, BN / 2);
-    const int grid2 = 2 * std::min(m_tiles2 * p.n_tiles, c.num_sms / 2);
+    const int grid2 = 2 * std::min(m_tiles2 * p.n_tiles, sms / 2);
     c.timer.begin(KC_GEMM, c.stream);
     switch (g.epi) {
       case TC_EPI_BIAS_ACT_SPLIT:
@@ -862,7 +863,7 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
     return 1;
   }
   const int total = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = std::min(total, c.num_sms);
+  const int grid = std::min(total, sms);
   c.timer.begin(KC_GEMM, c.stream);
   switch (g.epi) {
     case TC_EPI_BIAS_ACT_SPLIT:

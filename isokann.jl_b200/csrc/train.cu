@@ -201,10 +201,14 @@ struct OptHyper {
   int kind;
 };
 
+// The update runs over the index range [lo, hi) of the flat vector: the multi-GPU step reduces and updates the
+// gradient in two buckets (layers >= 2 first, while the backward pass of layer 1 is still running).
+// beta_dev (Adam): running (beta1^t, beta2^t) kept on the device so that a captured step can be replayed.
 __global__ void __launch_bounds__(256) optimiser_kernel(float *__restrict__ theta, const float *__restrict__ g,
                                                         float *__restrict__ m, float *__restrict__ v, int64_t P,
-                                                        OptHyper h, double *__restrict__ epoch_loss,
-                                                        int *__restrict__ flags) {
+                                                        int64_t lo, int64_t hi, OptHyper h,
+                                                        const float *__restrict__ beta_dev,
+                                                        double *__restrict__ epoch_loss, int *__restrict__ flags) {
   const double loss = (double)g[P] + (double)g[P + 1];
   const bool finite = (loss == loss) && (fabs(loss) != INFINITY);
   const bool poisoned = (*(volatile int *)flags & FLAG_NONFINITE_LOSS) != 0;
@@ -212,8 +216,9 @@ __global__ void __launch_bounds__(256) optimiser_kernel(float *__restrict__ thet
     if (blockIdx.x == 0 && threadIdx.x == 0 && !finite) atomicOr(flags, FLAG_NONFINITE_LOSS);
     return;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *epoch_loss += loss;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+  if (epoch_loss && blockIdx.x == 0 && threadIdx.x == 0) *epoch_loss += loss;
+  const float bt1 = beta_dev[0], bt2 = beta_dev[1];
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
     const float th = theta[i];
     const float gg = g[i] + h.lambda * th;
     float dx;
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(256) optimiser_kernel(float *__restrict__ thet
       const float vt = h.beta2 * v[i] + (1.0f - h.beta2) * (gg * gg);
       m[i] = mt;
       v[i] = vt;
-      dx = mt / (1.0f - h.bt1) / (sqrtf(vt / (1.0f - h.bt2)) + h.eps) * h.eta;
+      dx = mt / (1.0f - bt1) / (sqrtf(vt / (1.0f - bt2)) + h.eps) * h.eta;
     } else {
       const float vel = m[i];
       dx = -(h.rho * h.rho) * vel + (1.0f + h.rho) * h.eta * gg;
@@ -232,16 +237,40 @@ __global__ void __launch_bounds__(256) optimiser_kernel(float *__restrict__ thet
   }
 }
 
-void launch_optimiser(Ctx &c, int64_t P, float bt1, float bt2) {
-  OptHyper h{c.cfg.eta, c.cfg.lambda, c.cfg.beta1, c.cfg.beta2, c.cfg.eps, c.cfg.rho, bt1, bt2, c.cfg.optimiser};
-  int grid = (int)((P + 255) / 256);
+// beta^t <- beta^t * beta after a step whose loss was finite (the reference throws before update!, so a rejected
+// step leaves the optimiser state untouched); its own launch so that every block of the update saw the old value
+__global__ void advance_beta_kernel(float *__restrict__ beta_dev, float beta1, float beta2, const float *__restrict__ g,
+                                    int64_t P, const int *__restrict__ flags) {
+  const double loss = (double)g[P] + (double)g[P + 1];
+  const bool finite = (loss == loss) && (fabs(loss) != INFINITY);
+  if (!finite || (*flags & FLAG_NONFINITE_LOSS)) return;
+  beta_dev[0] *= beta1;
+  beta_dev[1] *= beta2;
+}
+
+void launch_optimiser_range(Ctx &c, int64_t lo, int64_t hi, bool accumulate_loss) {
+  if (hi <= lo) return;
+  OptHyper h{c.cfg.eta, c.cfg.lambda, c.cfg.beta1, c.cfg.beta2, c.cfg.eps, c.cfg.rho, 0.f, 0.f, c.cfg.optimiser};
+  int grid = (int)((hi - lo + 255) / 256);
   if (grid > c.num_sms * 8) grid = c.num_sms * 8;
   c.timer.begin(KC_OPT, c.stream);
-  optimiser_kernel<<<grid, 256, 0, c.stream>>>(c.params.p, c.grads.p, c.opt_m.p, c.opt_v.p, P, h, c.epoch_loss.p,
-                                               c.flags.p);
+  optimiser_kernel<<<grid, 256, 0, c.stream>>>(c.params.p, c.grads.p, c.opt_m.p, c.opt_v.p, c.P, lo, hi, h,
+                                               c.beta_dev.p, accumulate_loss ? c.epoch_loss.p : nullptr, c.flags.p);
   c.timer.end(c.stream);
   IK_CUDA(cudaGetLastError());
   c.count_launch(KC_OPT);
+}
+
+void launch_advance_beta(Ctx &c) {
+  if (c.cfg.optimiser != ISOKANN_OPT_ADAM) return;
+  advance_beta_kernel<<<1, 1, 0, c.stream>>>(c.beta_dev.p, c.cfg.beta1, c.cfg.beta2, c.grads.p, c.P, c.flags.p);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_OPT);
+}
+
+void launch_optimiser(Ctx &c, int64_t P) {
+  launch_optimiser_range(c, 0, P, true);
+  launch_advance_beta(c);
 }
 
 }  // namespace ik

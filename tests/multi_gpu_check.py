@@ -26,7 +26,9 @@ def main():
     for name, widths, target, N, K, B, gemm in [("c1", None, "shiftscale", 1003, 3, 250, "auto"),
                                                 ("c4", [231, 38, 6, 3], "pinv", 777, 2, 128, "auto"),
                                                 ("c4", [231, 38, 6, 2], "isa", 640, 2, 0, "auto"),
-                                                ("c1", [231, 256, 256, 1], "shiftscale", 900, 2, 300, "tc")]:
+                                                ("c1", [231, 256, 256, 1], "shiftscale", 900, 2, 300, "tc"),
+                                                ("c4", [231, 256, 264, 3], "pinv_default", 1200, 2, 400, "tc"),
+                                                ("c1", [231, 512, 1], "shiftscale", 700, 2, 0, "tc")]:
         w = copy.deepcopy(pkg.synthetic.WORKLOADS[name])
         if widths:
             w.widths = widths
@@ -34,7 +36,8 @@ def main():
         perms = pkg.synthetic.make_perms(w, N, 3)
         model = pkg.densenet(w.widths, layernorm=True, rng=np.random.default_rng(7))
         flat0 = model.flat()
-        tobj = {"shiftscale": pkg.TransformShiftscale, "isa": pkg.TransformISA, "pinv": pkg.TransformPseudoInv}[target]()
+        tobj = {"shiftscale": pkg.TransformShiftscale, "isa": pkg.TransformISA, "pinv": pkg.TransformPseudoInv,
+                "pinv_default": pkg.TransformPseudoInv}[target]()
         if target == "pinv":
             tobj = pkg.TransformPseudoInv(eigenvecs=False)   # Schur vectors are rounding-sensitive
 
@@ -68,6 +71,27 @@ def main():
         if not (np.array_equal(again.losses, multi.losses)
                 and np.array_equal(again.engine.download_params(), flat_m) and np.array_equal(pkg.chis(again), chi_m)):
             failures.append((name, "async upload differs", again.losses, multi.losses))
+        if gemm == "tc":
+            # the bucketed exchange beside the backward pass against the single-stream step with one all-reduce;
+            # plus a ragged last minibatch (partial=true) that leaves the last rank without rows
+            os.environ["ISOKANN_NO_COMM_OVERLAP"] = "1"
+            plain = make((world, rank, pkg.parallel.broadcast_unique_id(rank)))
+            del os.environ["ISOKANN_NO_COMM_OVERLAP"]
+            pkg.run_(plain, 3, perms=perms)
+            if not (np.allclose(plain.losses, multi.losses, rtol=1e-5)
+                    and np.abs(plain.engine.download_params() - flat_m).max() < 1e-4 * np.abs(flat_m).max()):
+                failures.append((name, "overlapped step differs from the single-stream step", plain.losses, multi.losses))
+            Br = N - 1 if B == 0 else (N - 1) // 2
+            for iso_ in (multi, single):
+                iso_.minibatch = Br
+                pkg.isotarget(iso_)
+            l_m = pkg.train_batch_(multi, perms[0], partial=True)
+            l_s = pkg.train_batch_(single, perms[0], partial=True)
+            if not (np.isclose(l_m, l_s, rtol=tol)
+                    and np.abs(multi.engine.download_params() - single.engine.download_params()).max()
+                    < tol * np.abs(flat_s).max()):
+                failures.append((name, "ragged last minibatch", l_m, l_s))
+            flat_m = multi.engine.download_params()
         # every rank must hold identical parameters
         t = torch.from_numpy(flat_m.copy()).cuda()
         ref = t.clone()
