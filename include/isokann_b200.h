@@ -112,6 +112,8 @@ typedef struct {
   double gemm_flops;         /* algorithmic 2*M*N*K of the GEMMs timed in ms_gemm             */
   double featurize_bytes;    /* algorithmic 4*(D+F)*M of the launches timed in ms_featurize   */
   double ms_nccl;            /* gradient all-reduces (includes waiting for the slowest rank)  */
+  int64_t graph_launches;    /* training epochs replayed as one captured CUDA graph; their kernels are
+                                counted in kernel_launches as well                                */
 } isokann_stats;
 
 int32_t isokann_abi_version(void);
@@ -217,6 +219,8 @@ int32_t isokann_download_grads(isokann_ctx *ctx, float *flat, int64_t P);
 int32_t isokann_target_matrices(isokann_ctx *ctx, float *kinv_colmajor, float *schur_colmajor,
                                 double *applied_rowmajor);
 
+/* on = 1: CUDA events around every kernel launch (per-class times in isokann_stats; training epochs run eagerly);
+ * on = 2: one event pair per phase only (ms_*_total), cheap enough to leave on; 0: off */
 int32_t isokann_enable_timing(isokann_ctx *ctx, int32_t on);
 int32_t isokann_get_stats(isokann_ctx *ctx, isokann_stats *out);
 int32_t isokann_reset_stats(isokann_ctx *ctx);

@@ -21,6 +21,10 @@ namespace ik {
 
 void EventTimer::begin(int cls, cudaStream_t s) {
   if (!enabled) return;
+  if (phases_only && !(cls >= KC_PHASE_KOOPMAN && cls <= KC_PHASE_TRAIN)) {
+    open.push_back((size_t)-1);  // keeps begin/end paired
+    return;
+  }
   if (used == pool.size()) {
     Pair p;
     cudaEventCreate(&p.a);
@@ -35,7 +39,7 @@ void EventTimer::begin(int cls, cudaStream_t s) {
 
 void EventTimer::end(cudaStream_t s) {
   if (!enabled || open.empty()) return;
-  cudaEventRecord(pool[open.back()].b, s);
+  if (open.back() != (size_t)-1) cudaEventRecord(pool[open.back()].b, s);
   open.pop_back();
 }
 
@@ -317,7 +321,7 @@ void comm_bucket_upper(Ctx &c);
 void backward_tc(Ctx &c, int64_t Bloc, bool head_done, bool overlap = false) {
   TcState &t = *c.tcs;
   const int L = c.L, d = c.d;
-  const int sms = c.num_sms - c.sm_reserve;
+  auto sms_now = [&] { return c.num_sms - c.sm_reserve; };  // the reserve changes once the upper bucket is under way
   tc_ensure_delta(c, Bloc);
   int cur = 0;
   {  // last (thin) layer
@@ -332,7 +336,7 @@ void backward_tc(Ctx &c, int64_t Bloc, bool head_done, bool overlap = false) {
     w.epi = TC_EPI_F32; w.act = ISOKANN_ACT_IDENTITY;
     w.ldc = d;
     const int tiles = cdiv(w.M, 128);
-    const int splits = std::max(1, std::min(sms / tiles, (int)(Bloc / 1024)));
+    const int splits = std::max(1, std::min(sms_now() / tiles, (int)(Bloc / 1024)));
     if (splits > 1) {
       c.splitk.ensure((size_t)splits * w.M * w.N);
       w.out_f32 = c.splitk.p;
@@ -363,7 +367,7 @@ void backward_tc(Ctx &c, int64_t Bloc, bool head_done, bool overlap = false) {
     w.ldc = fout;
     const int tiles = cdiv(w.M, 128) * cdiv(w.N, 256);
     // as many split-K slices as fit in ONE wave of CTAs (a partial second wave would double the kernel time)
-    int splits = std::max(1, std::min(sms / tiles, (int)(Bloc / 2048)));
+    int splits = std::max(1, std::min(sms_now() / tiles, (int)(Bloc / 2048)));
     if (splits > 1) {
       c.splitk.ensure((size_t)splits * w.M * w.N);
       w.out_f32 = c.splitk.p;
@@ -966,9 +970,11 @@ void comm_bucket_upper(Ctx &c) {
   allreduce_grads(c, lo, c.P + 2);
   launch_optimiser_range(c, lo, c.P, true);
   for (int l = 1; l + 1 < c.L; ++l) prep_layer_alt(c, l);
+  c.sm_reserve = c.comm_sms;  // the GEMMs launched from here to the end of the backward pass share the GPU with NCCL
 }
 
 void comm_bucket_lower(Ctx &c) {
+  c.sm_reserve = 0;  // nothing on the main stream overlaps the lower bucket but the next featurizer
   IK_CUDA(cudaEventRecord(c.ev_lower, c.stream));
   StreamScope on(c, c.comm_stream);
   IK_CUDA(cudaStreamWaitEvent(c.stream, c.ev_lower, 0));
@@ -999,6 +1005,7 @@ void train_step_overlapped(Ctx &c, int64_t s0, int64_t Bloc, int64_t len) {
     comm_bucket_lower(c);
     std::swap(t.wF, t.wF_alt);
     std::swap(t.wD, t.wD_alt);
+    c.weights_swapped = !c.weights_swapped;
     c.weights_in_flight = c.folded_valid = c.tc_weights_valid = true;
     return;
   }
@@ -1039,6 +1046,7 @@ void train_step_overlapped(Ctx &c, int64_t s0, int64_t Bloc, int64_t len) {
   comm_bucket_lower(c);
   std::swap(t.wF, t.wF_alt);
   std::swap(t.wD, t.wD_alt);
+  c.weights_swapped = !c.weights_swapped;
   c.weights_in_flight = true;   // the next reader of the parameters / operands waits for ev_weights
   c.folded_valid = true;
   c.tc_weights_valid = true;
@@ -1049,6 +1057,59 @@ void join_comm_stream(Ctx &c) {
   if (!c.weights_in_flight) return;
   IK_CUDA(cudaStreamWaitEvent(c.stream, c.ev_weights, 0));
   c.weights_in_flight = false;
+}
+
+// Capture the optimiser steps of one epoch into a CUDA graph.  Nothing is executed here; the caller launches the
+// instantiated graph.  Any failure leaves the context without a graph (the epoch then runs eagerly) and switches
+// capture off for this context.
+template <typename Steps>
+void capture_epoch(Ctx &c, Steps &&steps, int64_t N, int64_t bs, int64_t nb, bool overlap) {
+  Ctx::EpochGraph &g = c.egraph;
+  if (g.exec) {
+    cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+  }
+  const isokann_stats before = c.stats;
+  const bool fv = c.folded_valid, tv = c.tc_weights_valid, sw = c.weights_swapped;
+  const unsigned long long gen = alloc_generation();
+  cudaGraph_t graph = nullptr;
+  bool ok = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+  if (ok) {
+    try {
+      steps();
+    } catch (const ik::Error &) {
+      ok = false;
+    }
+    if (cudaStreamEndCapture(c.stream, &graph) != cudaSuccess || !graph) ok = false;
+  }
+  const bool realloc = gen != alloc_generation();  // a buffer grew during the capture: the graph holds stale pointers
+  if (ok && !realloc) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+  if (graph) cudaGraphDestroy(graph);
+  // the capture ran the host-side bookkeeping of the steps without running the steps: restore it
+  g.launches = c.stats.kernel_launches - before.kernel_launches;
+  g.nccl_calls = c.stats.nccl_calls - before.nccl_calls;
+  g.gemm_launches = c.stats.n_gemm_launches - before.n_gemm_launches;
+  g.feat_launches = c.stats.n_featurize_launches - before.n_featurize_launches;
+  c.stats = before;
+  c.folded_valid = fv;
+  c.tc_weights_valid = tv;
+  c.weights_in_flight = false;
+  if (c.tcs && c.weights_swapped != sw) {
+    std::swap(c.tcs->wF, c.tcs->wF_alt);
+    std::swap(c.tcs->wD, c.tcs->wD_alt);
+    c.weights_swapped = sw;
+  }
+  if (!ok || realloc) {
+    cudaGetLastError();
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+    if (!ok) c.graph_mode = 0;  // capture itself failed: stay eager; after a reallocation the next epoch retries
+    return;
+  }
+  g.N = N; g.bs = bs; g.nb = nb;
+  g.xs = c.xs; g.target = c.target.p; g.perm = c.perm_dev.p;
+  g.overlap = overlap;
+  g.alloc_gen = gen;
 }
 
 double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool partial) {
@@ -1086,12 +1147,53 @@ double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool par
       }
     } scope{c};
     c.comm_overlap = overlap;
-    c.sm_reserve = overlap ? c.comm_sms : 0;
-    for (int64_t i = 0; i < nb; ++i) {
-      const int64_t start = i * bs;
-      train_step(c, start, std::min(bs, N - start));
+    auto steps = [&] {
+      for (int64_t i = 0; i < nb; ++i) {
+        const int64_t start = i * bs;
+        train_step(c, start, std::min(bs, N - start));
+      }
+      join_comm_stream(c);
+    };
+    // canonical starting state of an epoch (what a captured graph assumes): operand sets in their original
+    // order and the folded / split weights current
+    if (c.tcs && c.weights_swapped) {
+      std::swap(c.tcs->wF, c.tcs->wF_alt);
+      std::swap(c.tcs->wD, c.tcs->wD_alt);
+      c.weights_swapped = false;
+      c.tc_weights_valid = false;
     }
-    join_comm_stream(c);
+    Ctx::EpochGraph &g = c.egraph;
+    const bool want_graph = c.graph_mode && (!c.timer.enabled || c.timer.phases_only) && nb >= 2;
+    const bool same = g.exec && g.N == N && g.bs == bs && g.nb == nb && g.xs == c.xs && g.target == c.target.p &&
+                      g.perm == c.perm_dev.p && g.overlap == overlap && g.alloc_gen == alloc_generation();
+    if (want_graph && (same || c.eager_epochs >= 1)) {
+      ensure_folded(c);
+      if (c.tc || c.tcn) ensure_tc_weights(c);
+      if (!same) capture_epoch(c, steps, N, bs, nb, overlap);
+    }
+    if (want_graph && g.exec && g.N == N && g.bs == bs && g.nb == nb && g.overlap == overlap &&
+        g.alloc_gen == alloc_generation() && g.xs == c.xs && g.target == c.target.p && g.perm == c.perm_dev.p) {
+      IK_CUDA(cudaGraphLaunch(g.exec, c.stream));
+      c.stats.kernel_launches += g.launches;
+      c.stats.nccl_calls += g.nccl_calls;
+      c.stats.n_gemm_launches += g.gemm_launches;
+      c.stats.n_featurize_launches += g.feat_launches;
+      c.stats.graph_launches++;
+      // host-side mirrors of what the replayed steps did
+      c.folded_valid = false;
+      c.tc_weights_valid = false;
+      if (overlap) {
+        c.folded_valid = c.tc_weights_valid = true;
+        if (nb & 1) {
+          std::swap(c.tcs->wF, c.tcs->wF_alt);
+          std::swap(c.tcs->wD, c.tcs->wD_alt);
+          c.weights_swapped = true;
+        }
+      }
+    } else {
+      steps();
+      c.eager_epochs++;
+    }
   }
   c.timer.end(c.stream);
   double *lp = read_back(c, c.epoch_loss.p, 1);
@@ -1380,6 +1482,7 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
     c->tcn = cfg->gemm_mode == ISOKANN_GEMM_AUTO && !tc_eligible(*cfg, true) && tcn_eligible(*cfg);
     c->fused_train = cfg->gemm_mode == ISOKANN_GEMM_AUTO && !tc_eligible(*cfg, true) && narrow_train_eligible(*cfg);
     c->tiny = cfg->gemm_mode == ISOKANN_GEMM_AUTO && tiny_forward_eligible(*cfg);
+    { const char *e = getenv("ISOKANN_GRAPH"); c->graph_mode = !(e && e[0] == '0'); }
     c->tc_no_pair = getenv("ISOKANN_TC_NO_PAIR") != nullptr;
     c->tc_no_head = getenv("ISOKANN_TC_NO_HEAD") != nullptr;
     { const char *e = getenv("ISOKANN_FEAT_REC"); c->feat_rec_off = e && e[0] == '0'; }
@@ -1426,6 +1529,7 @@ int32_t isokann_destroy(isokann_ctx *c) {
   if (!c) return ISOKANN_OK;
   cudaSetDevice(c->dev);
   cudaStreamSynchronize(c->stream);
+  if (c->egraph.exec) cudaGraphExecDestroy(c->egraph.exec);
   if (c->comm) nccl_comm_destroy(c->nccl, c->comm);
   c->timer.destroy();
   for (auto &a : c->act) a.release();
@@ -1919,6 +2023,7 @@ int32_t isokann_enable_timing(isokann_ctx *c, int32_t on) {
   return guarded(c, [&] {
     c->timer.flush(c->stream);
     c->timer.enabled = on != 0;
+    c->timer.phases_only = on == 2;  // 2: one event pair per phase only -- cheap enough for the timed pass
   });
 }
 

@@ -45,6 +45,7 @@ struct EventTimer {
     int cls;
   };
   bool enabled = false;
+  bool phases_only = false;  // record the three phase pairs only (isokann_enable_timing(ctx, 2))
   std::vector<Pair> pool;
   size_t used = 0;
   std::vector<size_t> open;
@@ -55,12 +56,20 @@ struct EventTimer {
   void destroy();
 };
 
+// bumped by every device (re)allocation: a captured epoch graph holds raw pointers and is only replayed while
+// this is unchanged since its capture
+inline unsigned long long &alloc_generation() {
+  static unsigned long long g = 0;
+  return g;
+}
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
   void ensure(size_t count) {
     if (count <= n) return;
+    ++alloc_generation();
     if (p) cudaFree(p);
     p = nullptr;
     n = 0;
@@ -68,7 +77,10 @@ struct DevBuf {
     n = count;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      cudaFree(p);
+      ++alloc_generation();
+    }
     p = nullptr;
     n = 0;
   }
@@ -265,8 +277,22 @@ struct Ctx {
   bool comm_overlap = false;      // set while train_epoch runs the overlapped step
   bool no_comm_overlap = false;   // ISOKANN_NO_COMM_OVERLAP=1: single-stream step with one all-reduce (A/B)
   bool weights_in_flight = false; // the communication stream still owes the refreshed parameters (ev_weights)
-  int comm_sms = 16;              // SMs the training-step GEMMs leave to NCCL (= NCCL_MAX_CTAS set at comm init)
+  int comm_sms = 8;               // SMs the training-step GEMMs leave to NCCL (= NCCL_MAX_CTAS set at comm init)
   int sm_reserve = 0;             // currently reserved (comm_sms during an overlapped epoch)
+
+  // the steps of one training epoch captured as a CUDA graph (train_epoch in api.cu): the offsets into the
+  // permutation are static for given (N, minibatch), so an epoch replays with one launch
+  struct EpochGraph {
+    cudaGraphExec_t exec = nullptr;
+    int64_t N = -1, bs = -1, nb = -1;
+    const void *xs = nullptr, *target = nullptr, *perm = nullptr;
+    unsigned long long alloc_gen = 0;
+    bool overlap = false;
+    int64_t launches = 0, nccl_calls = 0, gemm_launches = 0, feat_launches = 0;
+  } egraph;
+  int graph_mode = 1;          // ISOKANN_GRAPH=0 disables capture; epochs with kernel timers on run eagerly anyway
+  int64_t eager_epochs = 0;    // epochs run eagerly with the current shapes (the first one allocates: never captured)
+  bool weights_swapped = false;  // the operand sets wF/wD are exchanged relative to their canonical order
 
   // accounting
   isokann_stats stats{};

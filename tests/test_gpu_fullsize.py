@@ -99,22 +99,29 @@ def test_c5_shaped_optimiser_step(pkg, oracle):
     ysf = oracle.flatpairdists(records(ys))
     t_ref = oracle.isotarget_shiftscale(om, xsf, ysf)
     idx = perm - 1
-    l_ref, g_ref = oracle.batch_loss_and_grad(om, xsf[idx], t_ref[idx], None)
     blocks = param_blocks(w.widths, True)
     errs = {}
+    g_ref = None
     for opt in ("adam", "nesterov"):
         iso = make_iso(pkg, w, xs, ys, flat0, opt=opt, minibatch=0)
         t_lib = records(pkg.isotarget(iso))
         errs[f"{opt}.target"] = np.abs(t_lib - t_ref).max()
         assert np.allclose(t_lib, t_ref, atol=5e-4)                    # shiftscale divides by max - min ~ 0.05
+        if g_ref is None:
+            # training parity given the same target (the 5e-5 target difference above would otherwise show up as a
+            # 2e-4 relative difference of every delta): the oracle differentiates the loss against the library's target
+            l_ref, g_ref = oracle.batch_loss_and_grad(om, xsf[idx], t_lib[idx], None)
+            t_first = t_lib
+        assert np.array_equal(t_lib, t_first)                          # same weights, same target, whatever the rule
         loss = pkg.train_batch_(iso, perm)
-        assert np.isclose(loss, l_ref / N, rtol=2e-3), (loss, l_ref / N)   # target error enters the loss twice
+        errs[f"{opt}.loss"] = abs(loss - l_ref / N) / (l_ref / N)
+        assert np.isclose(loss, l_ref / N, rtol=1e-4), (loss, l_ref / N)
         g_lib = iso.engine.download_grads()
         for name, sl in blocks:
             scale = np.abs(g_ref[sl]).max()
             e = np.abs(g_lib[sl] - g_ref[sl]).max() / scale
             errs[f"{opt}.grad.{name}"] = e
-            assert e < 5e-3, (name, e)                                 # relative to the largest entry of the block
+            assert e < 2e-4, (name, e)                                 # relative to the largest entry of the block
         flat1 = iso.engine.download_params()
         cfg = oracle.OptConfig(kind=opt)
         st = oracle.opt_init(cfg, flat0.size)
@@ -126,7 +133,7 @@ def test_c5_shaped_optimiser_step(pkg, oracle):
         assert np.abs(flat1 - own1).max() < 1e-6
         if opt == "nesterov":   # linear in g: theta1 = theta0 - (1+rho)*eta*(g + lambda*theta0)
             errs["nesterov.params"] = np.abs(flat1 - ref1).max()
-            assert np.abs(flat1 - ref1).max() < 1.9e-3 * 5e-3 * np.abs(g_ref).max() + 1e-7
+            assert np.abs(flat1 - ref1).max() < 1.9e-3 * 2e-4 * np.abs(g_ref).max() + 1e-7
         else:                   # Adam's first step is eta*g'/(|g'|+eps): compare where the sign of g' is settled
             gp = g_ref + np.float32(1e-4) * flat0
             dpar = np.abs(flat1 - ref1)
