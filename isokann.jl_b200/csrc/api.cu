@@ -315,6 +315,12 @@ void tc_ensure_delta(Ctx &c, int64_t Bloc) {
 
 void comm_bucket_upper(Ctx &c);
 
+// The tensor core adds every MMA (K = 16) into the fp32 TMEM accumulator with truncation, so an accumulator that runs
+// over the whole minibatch picks up a bias of ~ (#MMAs) * 2^-24 relative to its magnitude: 5e-4 at 65 536 rows
+// (measured against the fp32 oracle, tests/test_gpu_fullsize.py).  Weight gradients therefore contract at most 4 096
+// rows per accumulator; the slices are summed in fp32 with round-to-nearest by splitk_reduce (fixed order).
+int wgrad_accuracy_splits(int64_t Bloc) { return (int)((Bloc + 4095) / 4096); }
+
 // head_done: launch_thin_head already produced delta_L (split, t.dlast) and delta_{L-1} (t.delta[0])
 // overlap: multi-rank step -- the gradients of layers >= 2 go to the communication stream as soon as the weight
 //          gradient of layer 2 has been launched (comm_bucket_upper)
@@ -336,7 +342,7 @@ void backward_tc(Ctx &c, int64_t Bloc, bool head_done, bool overlap = false) {
     w.epi = TC_EPI_F32; w.act = ISOKANN_ACT_IDENTITY;
     w.ldc = d;
     const int tiles = cdiv(w.M, 128);
-    const int splits = std::max(1, std::min(sms_now() / tiles, (int)(Bloc / 1024)));
+    const int splits = std::max(wgrad_accuracy_splits(Bloc), std::max(1, std::min(sms_now() / tiles, (int)(Bloc / 1024))));
     if (splits > 1) {
       c.splitk.ensure((size_t)splits * w.M * w.N);
       w.out_f32 = c.splitk.p;
@@ -367,7 +373,7 @@ void backward_tc(Ctx &c, int64_t Bloc, bool head_done, bool overlap = false) {
     w.ldc = fout;
     const int tiles = cdiv(w.M, 128) * cdiv(w.N, 256);
     // as many split-K slices as fit in ONE wave of CTAs (a partial second wave would double the kernel time)
-    int splits = std::max(1, std::min(sms_now() / tiles, (int)(Bloc / 2048)));
+    int splits = std::max(wgrad_accuracy_splits(Bloc), std::max(1, std::min(sms_now() / tiles, (int)(Bloc / 2048))));
     if (splits > 1) {
       c.splitk.ensure((size_t)splits * w.M * w.N);
       w.out_f32 = c.splitk.p;
