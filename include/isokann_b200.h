@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ISOKANN_ABI_VERSION 1
+#define ISOKANN_ABI_VERSION 2
 #define ISOKANN_MAX_LAYERS 8
 
 /* status codes; 1..4 are the reference's DomainErrors and must be re-thrown as such */
@@ -197,6 +197,17 @@ int32_t isokann_koopman(isokann_ctx *ctx, float *kchi_out);
 /* isotarget(target, model, xs, ys) (src/isotarget.jl:12,34,100-107,152-179); the target stays
  * resident for train_epoch; target_out (d x N) may be NULL */
 int32_t isokann_target(isokann_ctx *ctx, int32_t transform, const isokann_target_opts *opts, float *target_out);
+/* the resident target (d x N) of the last isokann_target / isokann_set_target, for loggers that look at it */
+int32_t isokann_download_target(isokann_ctx *ctx, float *target_out);
+/* validationloss(iso, valdata) (src/iso.jl:160-168): mean((chi(vx) - shiftscale([K chi(vy); K chi(ys)])[1:Nv])^2)
+ * in one call; vxs is D x Nv, vys is D x K x Nv (host, column-major).  Only the scalar leaves the device.
+ * One dimensional chi only (it shift-scales); ISOKANN_DOMAIN_CONSTANT_CHI as src/isotarget.jl:39. */
+int32_t isokann_validationloss(isokann_ctx *ctx, const float *vxs, const float *vys, int64_t D, int64_t K, int64_t Nv,
+                               double *loss_out);
+/* randperm(rng::Xoshiro, n) of Julia's Random stdlib (the draw Flux.DataLoader(shuffle=true) makes once per epoch,
+ * src/iso.jl:181): Xoshiro256++ state in/out (s0..s3 of the Xoshiro struct / task-local RNG), 1-based permutation
+ * out.  Host-side (the algorithm is inherently sequential).  UNPINNED against a real Julia session. */
+int32_t isokann_randperm(uint64_t *state4, int64_t n, int64_t *perm_out);
 /* user-defined isotarget methods: upload a d x N target computed on the host */
 int32_t isokann_set_target(isokann_ctx *ctx, const float *target, int64_t d, int64_t N);
 /* train_batch!(model, xs, target, opt, minibatch; shuffle, partial) (src/iso.jl:179-194).  perm

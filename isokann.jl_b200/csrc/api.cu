@@ -1542,7 +1542,7 @@ int32_t isokann_destroy(isokann_ctx *c) {
   DevBuf<float> *fb[] = {&c->params, &c->grads, &c->opt_m, &c->opt_v, &c->folded1, &c->gfold, &c->xs_own, &c->ys_own,
                          &c->kweights, &c->chi_x, &c->kchi, &c->kchi_loc, &c->gather_pad, &c->target, &c->w_loss,
                          &c->delta_a, &c->delta_b, &c->splitk, &c->staging_in, &c->staging_out, &c->red_f,
-                         &c->xs_stage};
+                         &c->xs_stage, &c->val_chi, &c->val_k1, &c->beta_dev};
   for (auto *b : fb) b->release();
   if (c->tcs) {
     for (auto &b : c->tcs->act) b.release();
@@ -1956,6 +1956,111 @@ int32_t isokann_target(isokann_ctx *c, int32_t transform, const isokann_target_o
     sync_stream(*c);
     c->timer.flush(c->stream);
   });
+}
+
+int32_t isokann_download_target(isokann_ctx *c, float *target_out) {
+  return guarded(c, [&] {
+    IK_REQUIRE(c->has_target && target_out, ISOKANN_ERR_STATE, "no resident target / NULL output");
+    IK_CUDA(cudaMemcpyAsync(target_out, c->target.p, (size_t)c->N * c->d * sizeof(float), cudaMemcpyDeviceToHost,
+                            c->stream));
+    sync_stream(*c);
+  });
+}
+
+// validationloss(iso, valdata) (src/iso.jl:160-168) with only scalars leaving the device:
+//   c = model(vx); k1 = expectation(model, vy); k2 = expectation(model, ys) on the resident data;
+//   SKc = shiftscale([k1; k2])[1:length(c)];  mean(abs2, c - SKc)
+int32_t isokann_validationloss(isokann_ctx *c, const float *vxs, const float *vys, int64_t D, int64_t K, int64_t Nv,
+                               double *loss_out) {
+  return guarded(c, [&] {
+    IK_REQUIRE(vxs && vys && loss_out && Nv > 0 && K > 0, ISOKANN_BAD_ARGUMENT, "NULL buffer or empty validation set");
+    IK_REQUIRE(D == c->D, ISOKANN_BAD_ARGUMENT, "coordinate dimension does not match the featurizer/model");
+    IK_REQUIRE(c->d == 1, ISOKANN_BAD_ARGUMENT, "validationloss shift-scales chi: one dimensional chi functions only");
+    Ctx &x = *c;
+    compute_koopman(x);  // k2 -> x.kchi (N)
+    x.val_chi.ensure((size_t)Nv);
+    x.val_k1.ensure((size_t)Nv);
+    const int64_t ch = chunk_rows(x, 1);
+    // chi on the validation start points
+    for (int64_t m0 = 0; m0 < Nv; m0 += ch) {
+      const int64_t m = std::min(ch, Nv - m0);
+      x.staging_in.ensure((size_t)m * D);
+      IK_CUDA(cudaMemcpyAsync(x.staging_in.p, vxs + m0 * D, (size_t)m * D * sizeof(float), cudaMemcpyHostToDevice,
+                              x.stream));
+      forward_rows(x, x.staging_in.p, nullptr, 0, m, true);
+      IK_CUDA(cudaMemcpyAsync(x.val_chi.p + m0, x.act[x.L].p, (size_t)m * sizeof(float), cudaMemcpyDeviceToDevice,
+                              x.stream));
+      sync_stream(x);  // the staging buffer is reused
+    }
+    // Koopman expectation on the validation samples, whole start points per chunk
+    const int64_t nsp = std::max<int64_t>(1, chunk_rows(x, K) / K);
+    for (int64_t n0 = 0; n0 < Nv; n0 += nsp) {
+      const int64_t ns = std::min(nsp, Nv - n0);
+      x.staging_in.ensure((size_t)ns * K * D);
+      IK_CUDA(cudaMemcpyAsync(x.staging_in.p, vys + n0 * K * D, (size_t)ns * K * D * sizeof(float),
+                              cudaMemcpyHostToDevice, x.stream));
+      forward_rows(x, x.staging_in.p, nullptr, 0, ns * K, true);
+      launch_kmean(x, x.act[x.L].p, nullptr, ns, (int)K, 1, x.val_k1.p + n0);
+      sync_stream(x);
+    }
+    // joint extrema of [k1; k2]
+    int nb1 = 0, nb2 = 0;
+    x.red_f.ensure(4 * 1024);
+    launch_minmax(x, x.val_k1.p, Nv, x.red_f.p, &nb1);
+    launch_minmax(x, x.kchi.p, x.N, x.red_f.p + 2 * nb1, &nb2);
+    float *mm = read_back(x, x.red_f.p, (size_t)2 * (nb1 + nb2));
+    float mn = INFINITY, mx = -INFINITY;
+    bool nan = false;
+    for (int b = 0; b < nb1 + nb2; ++b) {
+      nan = nan || mm[2 * b] != mm[2 * b] || mm[2 * b + 1] != mm[2 * b + 1];
+      mn = std::min(mn, mm[2 * b]);
+      mx = std::max(mx, mm[2 * b + 1]);
+    }
+    if (nan || !(mx > mn))
+      throw ik::Error{ISOKANN_DOMAIN_CONSTANT_CHI, "Could not compute the shift-scale. chi function is constant"};
+    int nb = 0;
+    launch_valloss(x, x.val_chi.p, x.val_k1.p, Nv, mn, mx, x.red_d.p, &nb);
+    double *part = read_back(x, x.red_d.p, (size_t)nb);
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b) s += part[b];
+    *loss_out = s / (double)Nv;
+    x.timer.flush(x.stream);
+  });
+}
+
+// Julia's randperm(rng::Xoshiro, n) replayed on the host (Random stdlib, Julia 1.12): Xoshiro256++ draws, the 52-bit
+// raw sample `rand(UInt64) >>> 12`, and randperm!'s inside-out shuffle with ltm52's masked rejection sampling
+// ("minibatch order").  UNPINNED: no golden vector from a Julia session is available in this environment;
+// tests compare it with an independent Python restatement of the same published algorithm.
+int32_t isokann_randperm(uint64_t *state4, int64_t n, int64_t *perm_out) {
+  if (!state4 || n < 0 || (n > 0 && !perm_out)) return ISOKANN_BAD_ARGUMENT;
+  uint64_t s0 = state4[0], s1 = state4[1], s2 = state4[2], s3 = state4[3];
+  auto rotl = [](uint64_t x, int k) { return (x << k) | (x >> (64 - k)); };
+  auto next = [&]() {
+    const uint64_t res = rotl(s0 + s3, 23) + s0;
+    const uint64_t t = s1 << 17;
+    s2 ^= s0;
+    s3 ^= s1;
+    s1 ^= s2;
+    s0 ^= s3;
+    s2 ^= t;
+    s3 = rotl(s3, 45);
+    return res;
+  };
+  if (n > 0) perm_out[0] = 1;
+  uint64_t mask = 3;
+  for (int64_t i = 2; i <= n; ++i) {
+    uint64_t x;
+    do {
+      x = (next() >> 12) & mask;           // ltm52(i, mask): masked 52-bit raw draw, rejected until <= i - 1
+    } while (x > (uint64_t)(i - 1));
+    const int64_t j = 1 + (int64_t)x;
+    if (i != j) perm_out[i - 1] = perm_out[j - 1];
+    perm_out[j - 1] = i;
+    if ((uint64_t)i == 1 + mask) mask = 2 * mask + 1;
+  }
+  state4[0] = s0; state4[1] = s1; state4[2] = s2; state4[3] = s3;
+  return ISOKANN_OK;
 }
 
 int32_t isokann_set_target(isokann_ctx *c, const float *target, int64_t d, int64_t N) {

@@ -141,6 +141,8 @@ void launch_kmean(Ctx &c, const float *chi, const float *weights, int64_t n, int
 void launch_minmax(Ctx &c, const float *x, int64_t n, float *partials, int *nblocks_out);
 void launch_shiftscale(Ctx &c, const float *x, int64_t n, const float *partials, int nblocks, float *out, int *flags);
 void launch_fill(Ctx &c, float *x, int64_t n, float v);
+void launch_valloss(Ctx &c, const float *chi, const float *k1, int64_t n, float mn, float mx, double *partials,
+                    int *nblocks_out);
 void launch_gram(Ctx &c, const float *chi, const float *kchi, int64_t n, int d, double *partials, int *nblocks_out);
 void launch_apply(Ctx &c, int mode, const float *kchi, const float *chi, int64_t n, int d, const Mat8 &mat,
                   float *target_out, double *partials, int *nblocks_out);
@@ -249,6 +251,7 @@ struct Ctx {
   DevBuf<float> xs_stage;          // send buffer of the padded xs all-gather (unequal shards)
   bool xs_gather_pending = false;  // multi-rank async upload: only this rank's rows of xs came from the host
   DevBuf<float> chi_x, kchi, kchi_loc, gather_pad, target, w_loss;
+  DevBuf<float> val_chi, val_k1;   // validationloss: chi and Koopman expectation on the validation points
   bool has_target = false;
   // d x d matrices of the last N-D target (isokann_target_matrices): Kinv / K and its real Schur vectors
   // (TransformPseudoInv, column-major like the reference's Julia matrices) and the final matrix applied to Kchi

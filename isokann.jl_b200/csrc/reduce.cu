@@ -340,6 +340,29 @@ void launch_isa_argmax(Ctx &c, const float *kchi, int64_t n, const IsaReplay &rp
 // host twin of the replay, used to rebuild the selected row exactly as the kernel saw it
 double isa_row_norm_host(const float *row, const IsaReplay &rp, double *xout) { return isa_row_norm(row, rp, xout); }
 
+// ---- validationloss (src/iso.jl:160-168): sum over the validation points of (c - (k1 - mn) / (mx - mn))^2 ----
+__global__ void valloss_kernel(const float *__restrict__ c, const float *__restrict__ k1, int64_t n, float mn, float mx,
+                               double *__restrict__ partials) {
+  double s = 0.0;
+  const float span = mx - mn;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float r = c[i] - (k1[i] - mn) / span;   // Float32 arithmetic like the reference's broadcast
+    s += (double)(r * r);
+  }
+  s = block_sum_d(s);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+void launch_valloss(Ctx &c, const float *chi, const float *k1, int64_t n, float mn, float mx, double *partials,
+                    int *nblocks_out) {
+  int grid = red_grid(c, n);
+  if (grid > 256) grid = 256;
+  valloss_kernel<<<grid, kRedThreads, 0, c.stream>>>(chi, k1, n, mn, mx, partials);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_REDUCE);
+  *nblocks_out = grid;
+}
+
 // ---- perm (1-based, Julia) -> 0-based device indices ----
 __global__ void perm0_kernel(const int64_t *__restrict__ p1, int64_t n, int64_t *__restrict__ p0) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)

@@ -274,6 +274,29 @@ class Engine:
         self._check(self.lib.isokann_target(self.h, L.TARGET[transform], C.byref(o), L.ptr(out)))
         return out
 
+    def download_target(self) -> np.ndarray:
+        out = np.empty((self.d, self.N), dtype=np.float32, order="F")
+        self._check(self.lib.isokann_download_target(self.h, L.ptr(out)))
+        return out
+
+    def validationloss(self, vxs, vys) -> float:
+        """validationloss(iso, valdata) (src/iso.jl:160-168) on the device; vxs (D, Nv), vys (D, K, Nv)"""
+        vxs, vys = julia_f32(vxs, 2), julia_f32(vys, 3)
+        D, K, Nv = vys.shape
+        out = C.c_double()
+        self._check(self.lib.isokann_validationloss(self.h, L.ptr(vxs), L.ptr(vys), D, K, Nv, C.byref(out)))
+        return out.value
+
+    @staticmethod
+    def randperm(state4, n: int):
+        """Julia's randperm(Xoshiro(s0, s1, s2, s3), n): returns (1-based permutation, advanced state)"""
+        st = np.ascontiguousarray(state4, dtype=np.uint64).copy()
+        out = np.empty(n, dtype=np.int64)
+        rc = L.load().isokann_randperm(L.ptr(st), int(n), L.ptr(out))
+        if rc != L.OK:
+            raise IsokannError(rc, "isokann_randperm: bad argument")
+        return out, st
+
     def set_target(self, target):
         t = julia_f32(target, 2)
         self._check(self.lib.isokann_set_target(self.h, L.ptr(t), t.shape[0], t.shape[1]))

@@ -159,19 +159,9 @@ def propchis(iso: Iso) -> np.ndarray:
 def validationloss(iso: Iso, valdata: SimulationData) -> float:
     """validationloss(iso, valdata) (src/iso.jl:160-168): mean squared difference between chi on the validation
     start points and the shift-scaled Koopman expectation, the shift-scale being estimated on validation and
-    training Koopman values together"""
+    training Koopman values together (isokann_validationloss)"""
     vx, vy = valdata.coords
-    c = iso.engine.forward(vx).ravel()
-    D, K, Nv = vy.shape
-    k1 = iso.engine.forward(vy.reshape(D, K * Nv, order="F")).reshape(K, Nv, order="F")
-    k1 = k1.astype(np.float32).sum(axis=0) / np.float32(K)
-    k2 = koopman(iso).ravel()
-    both = np.concatenate([k1, k2])
-    lo, hi = both.min(), both.max()
-    if not hi > lo:
-        raise DomainError(1, "Could not compute the shift-scale. chi function is constant")
-    skc = ((both - lo) / (hi - lo))[:c.size]
-    return float(np.mean((c - skc) ** 2))
+    return iso.engine.validationloss(vx, vy)     # one library call, only the scalar comes back
 
 
 def koopman(iso: Iso) -> np.ndarray:

@@ -100,6 +100,9 @@ SIGNATURES = {
     "isokann_chis": (C.c_int32, [_p, _p]),
     "isokann_koopman": (C.c_int32, [_p, _p]),
     "isokann_target": (C.c_int32, [_p, C.c_int32, C.POINTER(TargetOpts), _p]),
+    "isokann_download_target": (C.c_int32, [_p, _p]),
+    "isokann_validationloss": (C.c_int32, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64, _d]),
+    "isokann_randperm": (C.c_int32, [_p, C.c_int64, _p]),
     "isokann_set_target": (C.c_int32, [_p, _p, C.c_int64, C.c_int64]),
     "isokann_train_epoch": (C.c_int32, [_p, _p, C.c_int64, C.c_int32, _d]),
     "isokann_iterate": (C.c_int32, [_p, C.c_int32, C.POINTER(TargetOpts), C.c_int64, C.c_int64, C.c_int64, _p, _d]),

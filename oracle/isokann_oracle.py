@@ -30,7 +30,7 @@ __all__ = [
     "indexmap", "myisa", "fixperm", "isotarget_shiftscale", "isotarget_isa",
     "isotarget_pinv", "isotarget", "isa_from_chi", "pinv_from_chi", "OptConfig", "OptState", "opt_init",
     "opt_update", "loss_weights", "batch_loss_and_grad", "train_batch",
-    "run", "weighted_expectation", "chi_vjp",
+    "run", "weighted_expectation", "chi_vjp", "xoshiro256pp_next", "julia_randperm",
 ]
 
 F32 = np.float32
@@ -624,6 +624,55 @@ def run(m: Model, xsf: np.ndarray, ysf: np.ndarray, cfg: OptConfig, st: OptState
             losses.append(train_batch(m, xsf, t, cfg, st, minibatch, perms1[p]))
             p += 1
     return losses
+
+
+# ----------------------------------------------------------------------------------------------
+# minibatch order: Julia's randperm(rng::Xoshiro, n)  (Random stdlib of Julia 1.12; consumed by Flux.DataLoader at
+# src/iso.jl:181 through MLUtils.shuffleobs).  UNPINNED: restated from the published algorithm,
+# no golden vector from a Julia session is available here.  Pure-Python loops: small n only.
+# ----------------------------------------------------------------------------------------------
+
+_M64 = (1 << 64) - 1
+
+
+def xoshiro256pp_next(st: List[int]) -> int:
+    """one draw of Xoshiro256++ (Blackman & Vigna); st = [s0, s1, s2, s3] is advanced in place"""
+    def rotl(x, k):
+        return ((x << k) | (x >> (64 - k))) & _M64
+    s0, s1, s2, s3 = st
+    res = (rotl((s0 + s3) & _M64, 23) + s0) & _M64
+    t = (s1 << 17) & _M64
+    s2 ^= s0
+    s3 ^= s1
+    s1 ^= s2
+    s0 ^= s3
+    s2 ^= t
+    s3 = rotl(s3, 45)
+    st[:] = [s0, s1, s2, s3]
+    return res
+
+
+def julia_randperm(state4: Sequence[int], n: int):
+    """randperm!(rng, a) of Random: a[1] = 1; mask = 3; for i in 2:n: j = 1 + rand(rng, ltm52(i, mask));
+    a[i] = a[j]; a[j] = i; i == 1 + mask && (mask = 2mask + 1), where ltm52 draws (rand(UInt64) >>> 12) & mask until
+    the value is <= i - 1.  Returns (1-based permutation, advanced state)."""
+    st = [int(x) & _M64 for x in state4]
+    a = [0] * n
+    if n > 0:
+        a[0] = 1
+    mask = 3
+    for i in range(2, n + 1):
+        while True:
+            x = (xoshiro256pp_next(st) >> 12) & mask
+            if x <= i - 1:
+                break
+        j = 1 + x
+        if i != j:
+            a[i - 1] = a[j - 1]
+        a[j - 1] = i
+        if i == 1 + mask:
+            mask = 2 * mask + 1
+    return np.array(a, dtype=np.int64), st
 
 
 # ----------------------------------------------------------------------------------------------

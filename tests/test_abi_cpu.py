@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound(pkg):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in pkg.lib.SIGNATURES, f"{n} has no ctypes binding"
-    assert lib.isokann_abi_version() == 1
+    assert lib.isokann_abi_version() == 2
 
 
 def test_struct_layout_matches_header(pkg):
@@ -119,3 +119,40 @@ def test_model_flat_layout_roundtrip(pkg, oracle):
         assert wj.shape == wo.T.shape and np.array_equal(wj, wo.T)
     assert np.array_equal(ch.flat(), flat)
     assert ch.num_params() == oracle.num_params(om) == flat.size
+
+
+def test_randperm_matches_the_restated_julia_algorithm(pkg, oracle):
+    """isokann_randperm (host-side, no device needed) against the oracle's restatement of Julia's
+    randperm(rng::Xoshiro, n); both are UNPINNED against a real Julia session (no Julia here)."""
+    # Xoshiro256++ known answer: state (1, 2, 3, 4) -> rotl(1 + 4, 23) + 1
+    st = [1, 2, 3, 4]
+    assert oracle.xoshiro256pp_next(st) == (5 << 23) + 1
+    state = [0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB, 0x2545F4914F6CDD1D]
+    for n in (0, 1, 2, 3, 4, 5, 8, 9, 100, 4097):
+        got, st_lib = pkg.Engine.randperm(state, n)
+        ref, st_ref = oracle.julia_randperm(state, n)
+        assert np.array_equal(got, ref)
+        assert [int(x) for x in st_lib] == st_ref
+        assert sorted(got.tolist()) == list(range(1, n + 1))
+    # consecutive draws continue the stream (one randperm per epoch from the same task-local RNG)
+    a, st1 = pkg.Engine.randperm(state, 50)
+    b, _ = pkg.Engine.randperm(st1, 50)
+    ref_a, s1 = oracle.julia_randperm(state, 50)
+    ref_b, _ = oracle.julia_randperm(s1, 50)
+    assert np.array_equal(a, ref_a) and np.array_equal(b, ref_b) and not np.array_equal(a, b)
+
+
+def test_oracle_c_featurizer_matches_numpy(oracle):
+    """oracle/liboracle.so (C restatement used for large inputs) against the numpy gathers, bit for bit in float32"""
+    from oracle import isokann_oracle as io
+    rng = np.random.default_rng(0)
+    for A, M, dt in ((22, 300, np.float32), (35, 77, np.float64), (5, 1, np.float32)):
+        x = rng.normal(size=(M, 3 * A)).astype(dt)
+        pt = io.pair_table(A)
+        c = io._dists_from_pairs(x, pt, np.float32, use_c=True)
+        n = io._dists_from_pairs(x, pt, np.float32, use_c=False)
+        assert io._clib() is not None, "oracle/liboracle.so missing: run __graft_entry__.build()"
+        assert np.array_equal(c, n)
+    x = rng.normal(size=(4, 3, 18))
+    assert np.array_equal(io._dists_from_pairs(x, io.pair_table(6, [1, 3, 6]), np.float32, use_c=True),
+                          io._dists_from_pairs(x, io.pair_table(6, [1, 3, 6]), np.float32, use_c=False))
