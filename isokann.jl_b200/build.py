@@ -39,6 +39,28 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def nccl_include_dir() -> Path:
+    """nccl.h: $NCCL_INCLUDE_DIR, $NCCL_HOME/include, the nvidia-nccl wheel next to the running interpreter, or the
+    system include directory (the library itself is dlopen'ed at run time, csrc/nccl_dyn.cpp)"""
+    cands = []
+    if os.environ.get("NCCL_INCLUDE_DIR"):
+        cands.append(Path(os.environ["NCCL_INCLUDE_DIR"]))
+    if os.environ.get("NCCL_HOME"):
+        cands.append(Path(os.environ["NCCL_HOME"]) / "include")
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cands += [Path(p) / "include" for p in spec.submodule_search_locations]
+    except Exception:
+        pass
+    cands += [Path("/usr/include"), Path("/usr/local/cuda/include")]
+    for c in cands:
+        if (c / "nccl.h").exists():
+            return c
+    raise RuntimeError("nccl.h not found: set NCCL_INCLUDE_DIR or NCCL_HOME")
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source into one shared library.  Objects are cached per source."""
     dig = _digest()
@@ -48,9 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     objdir = HERE / "build"
     objdir.mkdir(exist_ok=True)
     incs = ["-I", str(HERE.parent / "include"), "-I", str(CSRC)]
-    nccl_inc = Path("/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/include")
-    if nccl_inc.exists():
-        incs += ["-I", str(nccl_inc)]
+    incs += ["-I", str(nccl_include_dir())]
     objs = []
     procs = []
     for src in sources():

@@ -830,10 +830,11 @@ struct StreamScope {
 };
 
 // in-place all-reduce(SUM) of grads[lo, hi) on the context's current stream
-void allreduce_grads(Ctx &c, int64_t lo, int64_t hi) {
+void allreduce_grads(Ctx &c, int64_t lo, int64_t hi, bool limited = false) {
   std::string err;
   c.timer.begin(KC_NCCL, c.stream);
-  int rc = nccl_allreduce_sum_f32(c.nccl, c.comm, c.grads.p + lo, (size_t)(hi - lo), c.stream, err);
+  void *comm = limited && c.comm_ov ? c.comm_ov : c.comm;
+  int rc = nccl_allreduce_sum_f32(c.nccl, comm, c.grads.p + lo, (size_t)(hi - lo), c.stream, err);
   c.timer.end(c.stream);
   IK_REQUIRE(rc == ISOKANN_OK, ISOKANN_ERR_NCCL, err);
   c.stats.nccl_calls++;
@@ -953,6 +954,52 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
 // ------------------------------------------------------------------------------------------
 void join_comm_stream(Ctx &c);
 
+// trace slots: main stream 0 step begin, 1 after featurizer, 2 weights ready, 3 after forward + head, 4 upper bucket
+// handed over, 5 backward done (lower bucket handed over); communication stream 6 upper all-reduce starts, 7 ends,
+// 8 upper optimiser + operands done, 9 lower all-reduce starts, 10 ends, 11 weights published
+constexpr int kTraceSlots = 12;
+void trace_mark(Ctx &c, int slot) {
+  if (!c.step_trace) return;
+  const size_t need = (size_t)(c.trace_steps + 1) * kTraceSlots;
+  while (c.trace_ev.size() < need) {
+    cudaEvent_t e;
+    IK_CUDA(cudaEventCreate(&e));
+    c.trace_ev.push_back(e);
+  }
+  IK_CUDA(cudaEventRecord(c.trace_ev[(size_t)c.trace_steps * kTraceSlots + slot], c.stream));
+}
+
+void trace_report(Ctx &c) {
+  if (!c.step_trace || c.trace_steps == 0) return;
+  IK_CUDA(cudaStreamSynchronize(c.stream));
+  if (c.comm_stream) IK_CUDA(cudaStreamSynchronize(c.comm_stream));
+  double acc[kTraceSlots] = {0};
+  double span = 0.0;
+  for (int st = 0; st < c.trace_steps; ++st) {
+    cudaEvent_t *e = &c.trace_ev[(size_t)st * kTraceSlots];
+    for (int k = 1; k < kTraceSlots; ++k) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e[0], e[k]) == cudaSuccess) acc[k] += ms;
+    }
+    if (st + 1 < c.trace_steps) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e[0], e[kTraceSlots]) == cudaSuccess) span += ms;
+    }
+  }
+  cudaGetLastError();
+  if (c.rank == 0) {
+    fprintf(stderr, "[isokann step trace] %d steps, us from step begin: featurized %.0f | weights ready %.0f | forward+head %.0f | "
+                    "upper handed over %.0f | backward done %.0f || comm: upper AR %.0f..%.0f, upper opt+prep done %.0f, "
+                    "lower AR %.0f..%.0f, weights published %.0f | step period %.0f\n",
+            c.trace_steps, 1e3 * acc[1] / c.trace_steps, 1e3 * acc[2] / c.trace_steps, 1e3 * acc[3] / c.trace_steps,
+            1e3 * acc[4] / c.trace_steps, 1e3 * acc[5] / c.trace_steps, 1e3 * acc[6] / c.trace_steps,
+            1e3 * acc[7] / c.trace_steps, 1e3 * acc[8] / c.trace_steps, 1e3 * acc[9] / c.trace_steps,
+            1e3 * acc[10] / c.trace_steps, 1e3 * acc[11] / c.trace_steps,
+            c.trace_steps > 1 ? 1e3 * span / (c.trace_steps - 1) : 0.0);
+  }
+  c.trace_steps = 0;
+}
+
 void ensure_comm_stream(Ctx &c) {
   if (c.comm_stream) return;
   IK_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
@@ -969,13 +1016,17 @@ void prep_layer_alt(Ctx &c, int l) {
 }
 
 void comm_bucket_upper(Ctx &c) {
+  trace_mark(c, 4);
   IK_CUDA(cudaEventRecord(c.ev_upper, c.stream));
   StreamScope on(c, c.comm_stream);
   IK_CUDA(cudaStreamWaitEvent(c.stream, c.ev_upper, 0));
   const int64_t lo = c.off_w[1];
-  allreduce_grads(c, lo, c.P + 2);
+  trace_mark(c, 6);
+  allreduce_grads(c, lo, c.P + 2, true);
+  trace_mark(c, 7);
   launch_optimiser_range(c, lo, c.P, true);
   for (int l = 1; l + 1 < c.L; ++l) prep_layer_alt(c, l);
+  trace_mark(c, 8);
   c.sm_reserve = c.comm_sms;  // the GEMMs launched from here to the end of the backward pass share the GPU with NCCL
 }
 
@@ -984,13 +1035,16 @@ void comm_bucket_lower(Ctx &c) {
   IK_CUDA(cudaEventRecord(c.ev_lower, c.stream));
   StreamScope on(c, c.comm_stream);
   IK_CUDA(cudaStreamWaitEvent(c.stream, c.ev_lower, 0));
+  trace_mark(c, 9);
   allreduce_grads(c, 0, c.off_w[1]);
+  trace_mark(c, 10);
   launch_optimiser_range(c, 0, c.off_w[1], false);
   launch_advance_beta(c);
   if (c.ln)
     launch_fold_ln(c, c.params.p + c.off_gamma, c.params.p + c.off_beta, c.params.p + c.off_w[0],
                    c.params.p + c.off_b[0], c.F, c.cfg.widths[1], c.folded1.p);
   prep_layer_alt(c, 0);
+  trace_mark(c, 11);
   IK_CUDA(cudaEventRecord(c.ev_weights, c.stream));
 }
 
@@ -1016,12 +1070,15 @@ void train_step_overlapped(Ctx &c, int64_t s0, int64_t Bloc, int64_t len) {
     return;
   }
   const bool pairs = c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
+  trace_mark(c, 0);
   // gather + featurizer of this minibatch: independent of the weights, so it runs beside the tail of the previous step
   launch_featurize_split(c, c.xs, c.perm_dev.p, s0, Bloc, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0]);
+  trace_mark(c, 1);
   if (c.weights_in_flight) {
     IK_CUDA(cudaStreamWaitEvent(c.stream, c.ev_weights, 0));
     c.weights_in_flight = false;
   }
+  trace_mark(c, 2);
   const bool head = !c.tc_no_head && thin_head_eligible(c);
   {
     struct Reset {
@@ -1044,12 +1101,15 @@ void train_step_overlapped(Ctx &c, int64_t s0, int64_t Bloc, int64_t len) {
     launch_loss_delta(c, c.act[L].p, c.target.p, c.perm_dev.p, s0, c.w_loss.p, Bloc, c.d, (double)len,
                       c.cfg.last_activation, c.delta_a.p, c.red_d.p, c.ticket.p, c.grads.p + c.P);
   }
+  trace_mark(c, 3);
   backward_tc(c, Bloc, head, true);
   if (c.ln)
     launch_unfold_ln(c, c.params.p + c.off_gamma, c.params.p + c.off_beta, c.params.p + c.off_w[0], c.gfold.p, c.F,
                      c.cfg.widths[1], c.grads.p + c.off_gamma, c.grads.p + c.off_beta, c.grads.p + c.off_w[0],
                      c.grads.p + c.off_b[0]);
+  trace_mark(c, 5);
   comm_bucket_lower(c);
+  if (c.step_trace) c.trace_steps++;
   std::swap(t.wF, t.wF_alt);
   std::swap(t.wD, t.wD_alt);
   c.weights_swapped = !c.weights_swapped;
@@ -1169,7 +1229,7 @@ double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool par
       c.tc_weights_valid = false;
     }
     Ctx::EpochGraph &g = c.egraph;
-    const bool want_graph = c.graph_mode && (!c.timer.enabled || c.timer.phases_only) && nb >= 2;
+    const bool want_graph = c.graph_mode && (!c.timer.enabled || c.timer.phases_only) && nb >= 2 && !c.step_trace;
     const bool same = g.exec && g.N == N && g.bs == bs && g.nb == nb && g.xs == c.xs && g.target == c.target.p &&
                       g.perm == c.perm_dev.p && g.overlap == overlap && g.alloc_gen == alloc_generation();
     if (want_graph && (same || c.eager_epochs >= 1)) {
@@ -1199,6 +1259,7 @@ double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool par
     } else {
       steps();
       c.eager_epochs++;
+      trace_report(c);
     }
   }
   c.timer.end(c.stream);
@@ -1536,6 +1597,8 @@ int32_t isokann_destroy(isokann_ctx *c) {
   cudaSetDevice(c->dev);
   cudaStreamSynchronize(c->stream);
   if (c->egraph.exec) cudaGraphExecDestroy(c->egraph.exec);
+  for (auto e : c->trace_ev) cudaEventDestroy(e);
+  if (c->comm_ov) nccl_comm_destroy(c->nccl, c->comm_ov);
   if (c->comm) nccl_comm_destroy(c->nccl, c->comm);
   c->timer.destroy();
   for (auto &a : c->act) a.release();
@@ -1627,14 +1690,17 @@ int32_t isokann_comm_init(isokann_ctx *c, int32_t world, int32_t rank, const voi
     // the gradient all-reduces run beside the GEMMs of the backward pass: bound the SMs NCCL may take and leave
     // exactly that many free (train_step_overlapped); a user setting of NCCL_MAX_CTAS is respected
     c->no_comm_overlap = getenv("ISOKANN_NO_COMM_OVERLAP") != nullptr;
+    c->step_trace = getenv("ISOKANN_STEP_TRACE") != nullptr;
     if (const char *e = getenv("ISOKANN_COMM_SMS")) c->comm_sms = std::max(0, std::min(64, atoi(e)));
-    if (!c->no_comm_overlap && c->comm_sms > 0) setenv("NCCL_MAX_CTAS", std::to_string(c->comm_sms).c_str(), 0);
-    if (const char *e = getenv("NCCL_MAX_CTAS")) c->comm_sms = std::max(0, std::min(64, atoi(e)));
     std::string err;
     c->nccl = nccl_load(err);
     IK_REQUIRE(c->nccl != nullptr, ISOKANN_ERR_NCCL, err);
     c->comm = nccl_comm_init(c->nccl, world, rank, id128, err);
     IK_REQUIRE(c->comm != nullptr, ISOKANN_ERR_NCCL, err);
+    // the bucket that is reduced beside the GEMMs of the backward pass uses a communicator limited to comm_sms
+    // CTAs (exactly the SMs those GEMMs leave free); everything else keeps NCCL's own choice
+    if (!c->no_comm_overlap && c->comm_sms > 0 && getenv("ISOKANN_COMM_SPLIT_OFF") == nullptr)
+      c->comm_ov = nccl_comm_split_limited(c->nccl, c->comm, rank, c->comm_sms);
     c->world = world;
     c->rank = rank;
   });

@@ -179,6 +179,7 @@ Nccl *nccl_load(std::string &err);
 int nccl_get_unique_id(Nccl *n, void *id128, std::string &err);
 void *nccl_comm_init(Nccl *n, int world, int rank, const void *id128, std::string &err);
 void nccl_comm_destroy(Nccl *n, void *comm);
+void *nccl_comm_split_limited(Nccl *n, void *comm, int rank, int max_ctas);
 int nccl_allreduce_sum_f32(Nccl *n, void *comm, float *buf, size_t count, cudaStream_t s, std::string &err);
 int nccl_allgather_f32(Nccl *n, void *comm, const float *send, float *recv, size_t count_per_rank, cudaStream_t s,
                        std::string &err);
@@ -273,6 +274,7 @@ struct Ctx {
   // multi-GPU
   Nccl *nccl = nullptr;
   void *comm = nullptr;
+  void *comm_ov = nullptr;   // same ranks, at most comm_sms CTAs per collective: the bucket that overlaps the GEMMs
   int world = 1, rank = 0;
   // bucketed gradient exchange beside the backward pass (train_step_overlapped in api.cu)
   cudaStream_t comm_stream = nullptr;
@@ -280,6 +282,11 @@ struct Ctx {
   bool comm_overlap = false;      // set while train_epoch runs the overlapped step
   bool no_comm_overlap = false;   // ISOKANN_NO_COMM_OVERLAP=1: single-stream step with one all-reduce (A/B)
   bool weights_in_flight = false; // the communication stream still owes the refreshed parameters (ev_weights)
+  // ISOKANN_STEP_TRACE=1: CUDA events at the joints of the overlapped step, averaged per epoch and printed to
+  // stderr by rank 0 (diagnostic; forces eager epochs)
+  bool step_trace = false;
+  std::vector<cudaEvent_t> trace_ev;  // [step][12]
+  int trace_steps = 0;
   int comm_sms = 8;               // SMs the training-step GEMMs leave to NCCL (= NCCL_MAX_CTAS set at comm init)
   int sm_reserve = 0;             // currently reserved (comm_sms during an overlapped epoch)
 

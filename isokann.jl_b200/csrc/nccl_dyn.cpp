@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -19,6 +20,7 @@ struct Nccl {
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, ncclConfig_t *) = nullptr;  // optional (NCCL >= 2.18)
 };
 
 static Nccl *g_nccl = nullptr;
@@ -26,11 +28,12 @@ static Nccl *g_nccl = nullptr;
 Nccl *nccl_load(std::string &err) {
   if (g_nccl) return g_nccl;
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
-  const char *names[] = {"libnccl.so.2", "libnccl.so",
-                         "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2",
+  // $ISOKANN_NCCL_LIB first; a libnccl already mapped into the process (e.g. by torch) is found by soname
+  const char *names[] = {getenv("ISOKANN_NCCL_LIB"), "libnccl.so.2", "libnccl.so",
                          "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
   void *h = nullptr;
   for (const char *nm : names) {
+    if (!nm || !nm[0]) continue;
     h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
     if (h) break;
   }
@@ -54,6 +57,7 @@ Nccl *nccl_load(std::string &err) {
   IK_SYM(AllGather, "ncclAllGather")
   IK_SYM(GetErrorString, "ncclGetErrorString")
 #undef IK_SYM
+  *(void **)(&n->CommSplit) = dlsym(h, "ncclCommSplit");
   g_nccl = n;
   return n;
 }
@@ -79,6 +83,18 @@ void *nccl_comm_init(Nccl *n, int world, int rank, const void *id128, std::strin
     return nullptr;
   }
   return (void *)comm;
+}
+
+// a second communicator over the same ranks whose kernels use at most max_ctas SMs (ncclCommSplit + ncclConfig_t):
+// the collectives that run beside the GEMMs of the backward pass go through it.  nullptr if unsupported.
+void *nccl_comm_split_limited(Nccl *n, void *comm, int rank, int max_ctas) {
+  if (!n || !comm || !n->CommSplit) return nullptr;
+  ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+  cfg.maxCTAs = max_ctas;
+  cfg.minCTAs = 1;
+  ncclComm_t out = nullptr;
+  if (n->CommSplit((ncclComm_t)comm, 0, rank, &out, &cfg) != ncclSuccess) return nullptr;
+  return (void *)out;
 }
 
 void nccl_comm_destroy(Nccl *n, void *comm) {
