@@ -114,6 +114,8 @@ typedef struct {
   double ms_nccl;            /* gradient all-reduces (includes waiting for the slowest rank)  */
   int64_t graph_launches;    /* training epochs replayed as one captured CUDA graph; their kernels are
                                 counted in kernel_launches as well                                */
+  int64_t p2p_exchanges;     /* gradient all-reduces done by the library's own NVLink peer-memory kernel
+                                (single node, CUDA IPC) instead of ncclAllReduce                     */
 } isokann_stats;
 
 int32_t isokann_abi_version(void);

@@ -821,6 +821,93 @@ int pick_splits(const Ctx &c, int Mout, int Nout, int Kred) {
   return std::min(s, 64);
 }
 
+// Map every rank's gradient buffer and flag block into this process (CUDA IPC; the 64-byte handles travel through
+// one NCCL all-gather).  All ranks agree on the outcome with an all-reduce, so either every rank uses the peer-memory
+// exchange or every rank stays on NCCL.
+void setup_p2p(Ctx &c) {
+  Ctx::P2P &q = c.p2p;
+  q.on = false;
+  if (c.world < 2 || c.world > ISOKANN_MAX_RANKS) return;
+  if (const char *e = getenv("ISOKANN_P2P_CTAS")) q.ctas = std::max(1, std::min(64, atoi(e)));
+  q.flag_block.ensure(2 * ISOKANN_MAX_RANKS);
+  q.seq.ensure(1);
+  q.ticket.ensure(1);
+  IK_CUDA(cudaMemset(q.flag_block.p, 0, 2 * ISOKANN_MAX_RANKS * sizeof(uint32_t)));
+  IK_CUDA(cudaMemset(q.seq.p, 0, sizeof(uint32_t)));
+  IK_CUDA(cudaMemset(q.ticket.p, 0, sizeof(unsigned int)));
+  constexpr int HF = (int)(sizeof(cudaIpcMemHandle_t) / sizeof(float));  // 16 floats per handle
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+  float send_h[2 * HF + 2];
+  float ok = 1.f;
+  cudaIpcMemHandle_t hg, hf;
+  if (cudaIpcGetMemHandle(&hg, c.grads.p) != cudaSuccess || cudaIpcGetMemHandle(&hf, q.flag_block.p) != cudaSuccess) {
+    cudaGetLastError();
+    ok = 0.f;
+    memset(&hg, 0, sizeof hg);
+    memset(&hf, 0, sizeof hf);
+  }
+  memcpy(send_h, &hg, 64);
+  memcpy(send_h + HF, &hf, 64);
+  send_h[2 * HF] = ok;
+  send_h[2 * HF + 1] = 0.f;
+  const int per = 2 * HF + 2;
+  DevBuf<float> xch;
+  xch.ensure((size_t)per * (c.world + 1));
+  IK_CUDA(cudaMemcpyAsync(xch.p, send_h, per * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+  std::string err;
+  int rc = nccl_allgather_f32(c.nccl, c.comm, xch.p, xch.p + per, (size_t)per, c.stream, err);
+  IK_REQUIRE(rc == ISOKANN_OK, ISOKANN_ERR_NCCL, err);
+  std::vector<float> all((size_t)per * c.world);
+  IK_CUDA(cudaMemcpyAsync(all.data(), xch.p + per, all.size() * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  sync_stream(c);
+  for (int p = 0; p < c.world && ok != 0.f; ++p) {
+    if (all[(size_t)p * per + 2 * HF] == 0.f) ok = 0.f;
+  }
+  for (int p = 0; p < c.world && ok != 0.f; ++p) {
+    if (p == c.rank) {
+      q.grads[p] = c.grads.p;
+      q.flags[p] = q.flag_block.p;
+      continue;
+    }
+    cudaIpcMemHandle_t a, b;
+    memcpy(&a, &all[(size_t)p * per], 64);
+    memcpy(&b, &all[(size_t)p * per + HF], 64);
+    void *pg = nullptr, *pf = nullptr;
+    if (cudaIpcOpenMemHandle(&pg, a, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0.f;
+      break;
+    }
+    q.opened.push_back(pg);
+    if (cudaIpcOpenMemHandle(&pf, b, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0.f;
+      break;
+    }
+    q.opened.push_back(pf);
+    q.grads[p] = (float *)pg;
+    q.flags[p] = (uint32_t *)pf;
+  }
+  // agreement: the exchange is used only if every rank mapped every peer
+  IK_CUDA(cudaMemcpyAsync(xch.p, &ok, sizeof(float), cudaMemcpyHostToDevice, c.stream));
+  rc = nccl_allgather_f32(c.nccl, c.comm, xch.p, xch.p + per, 1, c.stream, err);
+  IK_REQUIRE(rc == ISOKANN_OK, ISOKANN_ERR_NCCL, err);
+  std::vector<float> oks((size_t)c.world);
+  IK_CUDA(cudaMemcpyAsync(oks.data(), xch.p + per, oks.size() * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  sync_stream(c);
+  bool all_ok = true;
+  for (float v : oks) all_ok = all_ok && v != 0.f;
+  xch.release();
+  if (!all_ok) {
+    for (void *h : q.opened) cudaIpcCloseMemHandle(h);
+    q.opened.clear();
+    cudaGetLastError();
+    return;
+  }
+  q.on = true;
+  c.comm_sms = q.ctas;  // the overlapped GEMMs leave exactly the exchange kernel's CTAs free
+}
+
 // launch on another stream through the same wrappers; the context's stream is restored even if a launch throws
 struct StreamScope {
   Ctx &c;
@@ -831,6 +918,10 @@ struct StreamScope {
 
 // in-place all-reduce(SUM) of grads[lo, hi) on the context's current stream
 void allreduce_grads(Ctx &c, int64_t lo, int64_t hi, bool limited = false) {
+  if (c.p2p.on) {  // the library's own two-shot exchange over NVLink peer memory (csrc/p2p.cu)
+    launch_p2p_allreduce(c, lo, hi);
+    return;
+  }
   std::string err;
   c.timer.begin(KC_NCCL, c.stream);
   void *comm = limited && c.comm_ov ? c.comm_ov : c.comm;
@@ -1598,6 +1689,10 @@ int32_t isokann_destroy(isokann_ctx *c) {
   cudaStreamSynchronize(c->stream);
   if (c->egraph.exec) cudaGraphExecDestroy(c->egraph.exec);
   for (auto e : c->trace_ev) cudaEventDestroy(e);
+  for (void *h : c->p2p.opened) cudaIpcCloseMemHandle(h);
+  c->p2p.flag_block.release();
+  c->p2p.seq.release();
+  c->p2p.ticket.release();
   if (c->comm_ov) nccl_comm_destroy(c->nccl, c->comm_ov);
   if (c->comm) nccl_comm_destroy(c->nccl, c->comm);
   c->timer.destroy();
@@ -1701,6 +1796,9 @@ int32_t isokann_comm_init(isokann_ctx *c, int32_t world, int32_t rank, const voi
     // CTAs (exactly the SMs those GEMMs leave free); everything else keeps NCCL's own choice
     if (!c->no_comm_overlap && c->comm_sms > 0 && getenv("ISOKANN_COMM_SPLIT_OFF") == nullptr)
       c->comm_ov = nccl_comm_split_limited(c->nccl, c->comm, rank, c->comm_sms);
+    c->world = world;
+    c->rank = rank;
+    if (getenv("ISOKANN_NO_P2P") == nullptr) setup_p2p(*c);
     c->world = world;
     c->rank = rank;
   });

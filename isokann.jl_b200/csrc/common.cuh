@@ -29,6 +29,7 @@ struct Error {
   } while (0)
 
 constexpr int kMaxD = 8;  // largest chi dimension handled by the N-D target kernels
+#define ISOKANN_MAX_RANKS 16  // ranks of one NVSwitch node reachable through peer memory (csrc/p2p.cu)
 
 // device-side error flags (sticky until read by the host)
 enum : int { FLAG_CONSTANT_CHI = 1, FLAG_NONFINITE_LOSS = 2 };
@@ -164,6 +165,7 @@ void launch_tiny_forward(Ctx &c, const float *in, int64_t M, float *out);
 void launch_narrow_train(Ctx &c, const float *xhat, int64_t Bloc, const int64_t *idx, double Bglobal,
                          const float *seg0, float *g0);
 void launch_perm_to_zero_based(Ctx &c, const int64_t *perm1, int64_t n, int64_t *out0);
+void launch_p2p_allreduce(Ctx &c, int64_t lo, int64_t hi);  // in-place sum of grads[lo, hi) over all ranks
 void launch_compact_gather(Ctx &c, const float *padded, int world, int64_t nmax, int64_t N, int d, float *out);
 
 double isa_row_norm_host(const float *row, const IsaReplay &rp, double *xout);
@@ -287,6 +289,16 @@ struct Ctx {
   bool step_trace = false;
   std::vector<cudaEvent_t> trace_ev;  // [step][12]
   int trace_steps = 0;
+  // gradient exchange over CUDA-IPC peer memory (csrc/p2p.cu); falls back to NCCL when the mapping is not possible
+  struct P2P {
+    bool on = false;
+    int ctas = 16;                                  // CTAs of the exchange kernel = SMs the overlapped GEMMs leave free
+    float *grads[ISOKANN_MAX_RANKS] = {nullptr};    // every rank's gradient buffer mapped into this process
+    uint32_t *flags[ISOKANN_MAX_RANKS] = {nullptr}; // every rank's flag block
+    DevBuf<uint32_t> flag_block, seq;
+    DevBuf<unsigned int> ticket;
+    std::vector<void *> opened;                     // cudaIpcOpenMemHandle results to close
+  } p2p;
   int comm_sms = 8;               // SMs the training-step GEMMs leave to NCCL (= NCCL_MAX_CTAS set at comm init)
   int sm_reserve = 0;             // currently reserved (comm_sms during an overlapped epoch)
 

@@ -61,6 +61,18 @@ def main():
         st = multi.engine.stats()
         if not ok or st["nccl_calls"] == 0:
             failures.append((name, target, multi.losses, single.losses, float(np.abs(chi_m - chi_s).max())))
+        # the gradient exchange over NVLink peer memory (csrc/p2p.cu) against ncclAllReduce: with two ranks both add
+        # the same two numbers, so the runs must agree bit for bit
+        if st["p2p_exchanges"] == 0:
+            failures.append((name, "peer-memory exchange not in use", st))
+        os.environ["ISOKANN_NO_P2P"] = "1"
+        viaN = make((world, rank, pkg.parallel.broadcast_unique_id(rank)))
+        del os.environ["ISOKANN_NO_P2P"]
+        pkg.run_(viaN, 3, perms=perms)
+        if viaN.engine.stats()["p2p_exchanges"] != 0 or not (
+                np.array_equal(viaN.losses, multi.losses) and np.array_equal(viaN.engine.download_params(), flat_m)):
+            failures.append((name, "NCCL and peer-memory exchange differ", viaN.losses, multi.losses))
+        viaN.engine.close()
         # asynchronous upload: every rank sends only its own rows of xs over PCIe and fetches the rest from its peers
         # (in place for equal shards, padded otherwise); must reproduce the blocking upload bit for bit
         uid2 = pkg.parallel.broadcast_unique_id(rank)
