@@ -236,7 +236,7 @@ struct Ctx {
   cudaEvent_t xs_event = nullptr;  // xs rides the copy stream behind ys (only the training side reads it)
   // cudaFuncSetAttribute is per device: remembered per context, not per process (one process may hold contexts
   // on several devices)
-  enum { ATTR_FEAT_BWD = 0, ATTR_FEAT_LN, ATTR_FEAT_BLK0, ATTR_NARROW = 6, ATTR_TC1, ATTR_TC2 };
+  enum { ATTR_FEAT_BWD = 0, ATTR_FEAT_LN, ATTR_FEAT_BLK0, ATTR_NARROW = 6, ATTR_TC1, ATTR_TC2, ATTR_P2P };
   uint32_t func_attr_done = 0;
   bool attr_needed(int bit) {
     if (func_attr_done >> bit & 1u) return false;

@@ -65,9 +65,16 @@ struct P2PArgs {
   int rank, world;
 };
 
+// The peer loads are cp.async copies into shared memory (16 bytes each, no destination register, so nothing limits how
+// many are in flight): every thread fetches the W copies of its element, two elements deep (double-buffered), and
+// consumes only what it fetched itself, so a cp.async.wait_group is all the synchronisation the pipeline needs.  An
+// earlier version loaded into registers: ptxas kept 2-3 loads in flight per thread and 16.8 MB on 8 GPUs took 355 us.
+// WT: world size at compile time (2, 4, 8) or 0 for any world size.
+template <int WT>
 __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(P2PArgs a) {
+  extern __shared__ __align__(16) float4 stage[];  // [2][W][kP2PThreads]
   __shared__ bool is_last;
-  const int W = a.world;
+  const int W = WT ? WT : a.world;
   const uint32_t seq = *((volatile uint32_t *)a.seq) + 1u;
   // ---- ready: the kernels before this one in stream order produced the local gradient
   if (blockIdx.x == 0 && threadIdx.x < W) {
@@ -83,17 +90,40 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(P2PArgs a) {
     const int64_t nvec = (hi4 - lo4) >> 2;
     const int64_t per = (nvec + W - 1) / W;
     const int64_t v0 = min(nvec, per * a.rank), v1 = min(nvec, v0 + per);
-    for (int64_t v = v0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < v1; v += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t i = lo4 + (v << 2);
-      float4 s = ld_peer4(a.grads[0] + i);
-#pragma unroll 1
-      for (int p = 1; p < W; ++p) {
-        const float4 x = ld_peer4(a.grads[p] + i);
-        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage) + 16u * threadIdx.x;
+    auto fetch = [&](int64_t v, int buf) {
+      if (v < v1) {
+        const int64_t i = lo4 + (v << 2);
+#pragma unroll
+        for (int p = 0; p < (WT ? WT : ISOKANN_MAX_RANKS); ++p)
+          if (p < W)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * kP2PThreads * (buf * W + p)),
+                         "l"(a.grads[p] + i)
+                         : "memory");
       }
-#pragma unroll 1
-      for (int p = 0; p < W; ++p) *reinterpret_cast<float4 *>(a.grads[p] + i) = s;
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int64_t v = v0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int buf = 0;
+    fetch(v, 0);
+    for (; v < v1; v += stride, buf ^= 1) {
+      fetch(v + stride, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      const float4 *x = stage + (size_t)kP2PThreads * (buf * W) + threadIdx.x;
+      float4 s = x[0];
+#pragma unroll
+      for (int p = 1; p < (WT ? WT : ISOKANN_MAX_RANKS); ++p)
+        if (p < W) {  // summed in rank order
+          const float4 y = x[(size_t)kP2PThreads * p];
+          s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
+        }
+      const int64_t i = lo4 + (v << 2);
+#pragma unroll
+      for (int p = 0; p < (WT ? WT : ISOKANN_MAX_RANKS); ++p)
+        if (p < W) *reinterpret_cast<float4 *>(a.grads[p] + i) = s;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   if (a.rank == 0 && blockIdx.x == 0) {
     const int64_t head = min(lo4, a.hi) - a.lo, tail = a.hi - max(hi4, min(lo4, a.hi));
@@ -143,8 +173,21 @@ void launch_p2p_allreduce(Ctx &c, int64_t lo, int64_t hi) {
   // the overlapped GEMMs leave SMs free
   const int64_t nvec = (hi - lo) / 4;
   int grid = (int)std::max<int64_t>(1, std::min<int64_t>(c.p2p.ctas, (nvec / c.world + kP2PThreads - 1) / kP2PThreads));
+  const size_t smem = (size_t)2 * c.world * kP2PThreads * sizeof(float4);
+  if (c.attr_needed(Ctx::ATTR_P2P)) {
+    IK_CUDA(cudaFuncSetAttribute(p2p_allreduce_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    IK_CUDA(cudaFuncSetAttribute(p2p_allreduce_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    IK_CUDA(cudaFuncSetAttribute(p2p_allreduce_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    IK_CUDA(cudaFuncSetAttribute(p2p_allreduce_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+  }
+  IK_REQUIRE(smem <= 208 * 1024, ISOKANN_ERR_STATE, "peer-memory exchange: world size too large for the staging buffer");
   c.timer.begin(KC_NCCL, c.stream);
-  p2p_allreduce_kernel<<<grid, kP2PThreads, 0, c.stream>>>(a);
+  switch (c.world) {
+    case 2: p2p_allreduce_kernel<2><<<grid, kP2PThreads, smem, c.stream>>>(a); break;
+    case 4: p2p_allreduce_kernel<4><<<grid, kP2PThreads, smem, c.stream>>>(a); break;
+    case 8: p2p_allreduce_kernel<8><<<grid, kP2PThreads, smem, c.stream>>>(a); break;
+    default: p2p_allreduce_kernel<0><<<grid, kP2PThreads, smem, c.stream>>>(a); break;
+  }
   c.timer.end(c.stream);
   IK_CUDA(cudaGetLastError());
   c.count_launch(KC_REDUCE);
