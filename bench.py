@@ -45,8 +45,12 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "koopman_samples_per_s_per_isokann_iteration"
 UNIT = "samples/s"
-DTYPE_NOTE = ("fp32 storage and accumulation; wide Dense layers multiply split-bf16 operands on tcgen05 (3 MMAs per "
-              "product: hi*hi + hi*lo + lo*hi, lo*lo dropped), narrow layers run FP32 FFMA")
+def dtype_note():
+    fwd = os.environ.get("ISOKANN_TC_FWD", "bf16x3")
+    return ("fp32 storage and accumulation; wide Dense layers multiply split 16-bit operands on tcgen05: training "
+            "steps bf16 pairs x 3 MMAs (hi*hi + hi*lo + lo*hi), inference forward (Koopman pass, chis) "
+            + ("fp16 pairs x 2 MMAs (hi*hi + lo*hi, weights rounded once to fp16)" if fwd == "fp16x2"
+               else "bf16 pairs x 3 MMAs") + "; narrow layers run FP32 FFMA")
 
 
 def parse():
@@ -61,6 +65,8 @@ def parse():
     ap.add_argument("--minibatch", type=int, default=None)
     ap.add_argument("--target", default=None, choices=["shiftscale", "isa", "pinv"])
     ap.add_argument("--gemm", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--tc-fwd", default=None, choices=["bf16x3", "fp16x2"],
+                    help="operand format of the inference forward of the wide layers (default: the library's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the c2/c3/c4 entries of `configs`")
     ap.add_argument("--profile", action="store_true",
@@ -83,7 +89,7 @@ def workload_config(w, N, K, B, target, extra=None):
     cfg = {"workload": f"{w.name}: {w.n_atoms}-atom pairdist featurizer F={w.F}, pairnet {w.widths}, N={N}, K={K}, "
                        f"{target} target, {w.opt}, minibatch={B}",
            "N": N, "K": K, "minibatch": B, "widths": list(w.widths), "target": target, "optimiser": w.opt,
-           "arithmetic": DTYPE_NOTE,
+           "arithmetic": dtype_note(),
            "l2": "inputs (coords of K*N samples) larger than the 126 MB L2" if N * K * w.D * 4 > 126e6
                  else "inputs fit in L2; steady-state iteration"}
     if extra:
@@ -404,6 +410,8 @@ def run_b200(args, pkg):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
+    if args.tc_fwd:
+        os.environ["ISOKANN_TC_FWD"] = args.tc_fwd
     w = pkg.synthetic.WORKLOADS[args.config]
     N = args.N or w.N
     K = args.K or w.K
@@ -483,13 +491,15 @@ def run_b200(args, pkg):
         ach = st["gemm_flops"] / (st["ms_gemm"] * 1e-3) / 1e12 if st["ms_gemm"] > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "dense-layer GEMM (fused bias+activation)", "achieved": ach,
                 "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": traffic,
-                "executed_tflops": 3 * ach,
+                "executed_tflops": (st["gemm_mma_flops"] / (st["ms_gemm"] * 1e-3) / 1e12) if st["ms_gemm"] > 0 else 0.0,
+                "mmas_per_product": st["gemm_mma_flops"] / st["gemm_flops"] if st["gemm_flops"] > 0 else None,
                 "peak_source": f"{pk['src']} bf16 sustained", "launches": st["n_gemm_launches"],
                 "avg_launch_ms": st["ms_gemm"] / max(1, st["n_gemm_launches"]),
-                "note": "algorithmic 2*M*N*K flops of all GEMM launches / their CUDA-event time; every k-slice is "
-                        "3 bf16 MMAs (hi*hi, hi*lo, lo*hi) to keep fp32 accuracy, so frac <= 1/3 by construction and "
-                        "executed_tflops = 3*achieved is what the tensor pipe runs; traffic = mean dram bytes per "
-                        "launch from profiles/traffic.json (ncu)"}
+                "note": "algorithmic 2*M*N*K flops of all GEMM launches / their CUDA-event time; every product costs "
+                        "mmas_per_product 16-bit MMAs (3 = hi*hi + hi*lo + lo*hi on bf16 pairs; 2 = hi*hi + lo*hi on "
+                        "fp16 pairs with the weights rounded once, inference forward only) to stay inside the fp32 "
+                        "tolerance, so frac <= 1/mmas_per_product by construction and executed_tflops is what the "
+                        "tensor pipe runs; traffic = mean dram bytes per launch from profiles/traffic.json (ncu)"}
     else:
         roof = hbm_roofline(w, N, K, ms / nsteps, pk, target != "shiftscale")
     # the other kernel north_star asks a roofline figure for: the featurizer against measured HBM bandwidth

@@ -114,6 +114,7 @@ typedef struct {
   double ms_nccl;            /* gradient all-reduces (includes waiting for the slowest rank)  */
   int64_t graph_launches;    /* training epochs replayed as one captured CUDA graph; their kernels are
                                 counted in kernel_launches as well                                */
+  double gemm_mma_flops;     /* flops the tensor pipe executed for gemm_flops (2 or 3 MMAs per product)   */
   int64_t p2p_exchanges;     /* gradient all-reduces done by the library's own NVLink peer-memory kernel
                                 (single node, CUDA IPC) instead of ncclAllReduce                     */
 } isokann_stats;

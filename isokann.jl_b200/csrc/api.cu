@@ -237,14 +237,34 @@ void ensure_tc_weights(Ctx &c) {
   c.tc_weights_valid = true;
 }
 
+// fp16 copies of the forward operands for the 2-MMA inference forward (regenerated lazily after an update)
+void ensure_wf16(Ctx &c) {
+  if (c.wf16_valid) return;
+  ensure_folded(c);
+  TcState &t = *c.tcs;
+  t.wF16.resize(c.L);
+  for (int l = 0; l + 1 < c.L; ++l) {
+    const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
+    t.wF16[l].ensure((size_t)fout * t.wp[l]);
+    launch_prep_weights_f16(c, layer_segment(c, l), fin, fout, t.wF16[l].p, t.wp[l]);
+  }
+  c.wf16_valid = true;
+}
+
 // x_pre: x_hat of these rows already featurized (on another stream) into that buffer
+// Inference (keep == false) may run in the fp16 / 2-MMA mode (Ctx::fwd_fp16x2): activations as fp16 (hi, lo) pairs,
+// weights rounded once to fp16, hi*hi + lo*hi per product.  The training forward always keeps bf16 x 3: its
+// activations are operands of the weight-gradient GEMMs together with bf16 deltas.
 void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords,
                      bool keep, const SplitBuf *x_pre) {
   TcState &t = *c.tcs;
   tc_ensure_rows(c, M);
-  ensure_tc_weights(c);
+  const bool h2 = c.fwd_fp16x2 && !keep;
+  if (h2) ensure_wf16(c);
+  else ensure_tc_weights(c);
   const bool pairs = in_is_coords && c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
-  if (!x_pre) launch_featurize_split(c, in, gather, goff, M, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0]);
+  if (!x_pre)
+    launch_featurize_split(c, in, gather, goff, M, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0], h2 ? 1 : 0);
   const SplitBuf &x0 = x_pre ? *x_pre : t.act[0];
   const int last = c.L - 1;
   const float *seg_last = c.params.p + c.off_w[last];
@@ -252,7 +272,14 @@ void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t gof
     const int fin = c.cfg.widths[l], fout = c.cfg.widths[l + 1];
     TcGemm g{};
     g.a_hi = l == 0 ? x0.hi.p : t.act[l].hi.p; g.a_lo = l == 0 ? x0.lo.p : t.act[l].lo.p; g.lda = t.wp[l];
-    g.b_hi = t.wF[l].hi.p; g.b_lo = t.wF[l].lo.p; g.ldb = t.wp[l];
+    if (h2) {
+      g.b_hi = g.b_lo = t.wF16[l].p;
+      g.fmt = 1;
+      g.nmma = 2;
+    } else {
+      g.b_hi = t.wF[l].hi.p; g.b_lo = t.wF[l].lo.p;
+    }
+    g.ldb = t.wp[l];
     g.M = (int)M; g.N = fout; g.K = fin;
     g.act = c.cfg.activation;
     g.bias = layer_segment(c, l) + (int64_t)fin * fout;
@@ -269,7 +296,7 @@ void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t gof
       return;
     }
     g.epi = TC_EPI_BIAS_ACT_SPLIT;
-    g.ones_col = 1;
+    g.ones_col = h2 ? 0 : 1;  // the fp16 pass never feeds a weight gradient; the training forward rewrites the column
     g.out_hi = t.act[l + 1].hi.p; g.out_lo = t.act[l + 1].lo.p; g.ldo = t.wp[l + 1];
     launch_tc_gemm(c, g);
   }
@@ -508,7 +535,8 @@ void compute_koopman(Ctx &c) {
       IK_CUDA(cudaEventCreateWithFlags(&t.koop_start, cudaEventDisableTiming));
     }
     tc_ensure_rows(c, ch);
-    ensure_tc_weights(c);
+    if (c.fwd_fp16x2) ensure_wf16(c);
+    else ensure_tc_weights(c);
     t.x_alt.ensure(ch, t.wp[0]);
     SplitBuf *bufs[2] = {&t.act[0], &t.x_alt};
     IK_CUDA(cudaEventRecord(t.koop_start, c.stream));
@@ -529,7 +557,7 @@ void compute_koopman(Ctx &c) {
         } back{c.stream, t.feat_stream};
         std::swap(c.stream, t.feat_stream);
         launch_featurize_split(c, c.ys + n0 * c.K * c.D, nullptr, 0, ns * c.K, pairs, c.ln, bufs[b]->hi.p,
-                               bufs[b]->lo.p, t.wp[0]);
+                               bufs[b]->lo.p, t.wp[0], c.fwd_fp16x2 ? 1 : 0);
       }
       IK_CUDA(cudaEventRecord(t.feat_done[b], t.feat_stream));
       IK_CUDA(cudaStreamWaitEvent(c.stream, t.feat_done[b], 0));
@@ -1028,6 +1056,7 @@ void train_step(Ctx &c, int64_t start, int64_t len) {
   launch_optimiser(c, c.P);
   c.folded_valid = false;
   c.tc_weights_valid = false;
+  c.wf16_valid = false;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1158,6 +1187,7 @@ void train_step_overlapped(Ctx &c, int64_t s0, int64_t Bloc, int64_t len) {
     std::swap(t.wD, t.wD_alt);
     c.weights_swapped = !c.weights_swapped;
     c.weights_in_flight = c.folded_valid = c.tc_weights_valid = true;
+    c.wf16_valid = false;
     return;
   }
   const bool pairs = c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
@@ -1207,6 +1237,7 @@ void train_step_overlapped(Ctx &c, int64_t s0, int64_t Bloc, int64_t len) {
   c.weights_in_flight = true;   // the next reader of the parameters / operands waits for ev_weights
   c.folded_valid = true;
   c.tc_weights_valid = true;
+  c.wf16_valid = false;
 }
 
 // order the main stream behind the communication stream (end of an epoch, or before anything else reads the model)
@@ -1339,6 +1370,7 @@ double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool par
       // host-side mirrors of what the replayed steps did
       c.folded_valid = false;
       c.tc_weights_valid = false;
+      c.wf16_valid = false;
       if (overlap) {
         c.folded_valid = c.tc_weights_valid = true;
         if (nb & 1) {
@@ -1641,6 +1673,7 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
     c->fused_train = cfg->gemm_mode == ISOKANN_GEMM_AUTO && !tc_eligible(*cfg, true) && narrow_train_eligible(*cfg);
     c->tiny = cfg->gemm_mode == ISOKANN_GEMM_AUTO && tiny_forward_eligible(*cfg);
     { const char *e = getenv("ISOKANN_GRAPH"); c->graph_mode = !(e && e[0] == '0'); }
+    { const char *e = getenv("ISOKANN_TC_FWD"); c->fwd_fp16x2 = e && strcmp(e, "fp16x2") == 0; }
     c->tc_no_pair = getenv("ISOKANN_TC_NO_PAIR") != nullptr;
     c->tc_no_head = getenv("ISOKANN_TC_NO_HEAD") != nullptr;
     { const char *e = getenv("ISOKANN_FEAT_REC"); c->feat_rec_off = e && e[0] == '0'; }
@@ -1708,6 +1741,7 @@ int32_t isokann_destroy(isokann_ctx *c) {
     for (auto &b : c->tcs->wD) b.release();
     for (auto &b : c->tcs->wF_alt) b.release();
     for (auto &b : c->tcs->wD_alt) b.release();
+    for (auto &b : c->tcs->wF16) b.release();
     c->tcs->delta[0].release();
     c->tcs->delta[1].release();
     c->tcs->dot_partial.release();
@@ -1952,6 +1986,7 @@ int32_t isokann_upload_params(isokann_ctx *c, const float *flat, int64_t P) {
     sync_stream(*c);
     c->folded_valid = false;
     c->tc_weights_valid = false;
+    c->wf16_valid = false;
   });
 }
 

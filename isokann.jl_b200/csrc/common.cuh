@@ -209,6 +209,9 @@ struct Ctx {
   bool fused_train = false;   // narrow net + small minibatch: one fused fwd/loss/bwd kernel per step
   bool tcn = false;           // narrow net: inference forward = one tcgen05 GEMM with the MLP tail in its epilogue
   bool tc_weights_valid = false;
+  int split_fmt = 0;          // format the split featurizer kernels write (0 bf16 pairs, 1 fp16 pairs); set per launch
+  bool fwd_fp16x2 = false;    // inference forward of the wide layers: fp16 operands, 2 MMAs per product
+  bool wf16_valid = false;    // tcs->wF16 matches the current parameters
   int tri_n = 0;            // atoms of an upper-triangle featurizer (all pairs / atom subset), else 0
   DevBuf<int> tri_cmap;     // atom subset: coordinate c of the selection -> coordinate of the record (else null)
   bool feat_rec_off = false;  // ISOKANN_FEAT_REC=0: keep the lane = feature kernel (A/B comparison)

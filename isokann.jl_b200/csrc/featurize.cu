@@ -9,6 +9,8 @@
 // mean/variance, and the normalised row is written back coalesced.
 //
 // Algorithmic HBM traffic per record: 4*D read + 4*F written.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -26,7 +28,7 @@ __global__ void __launch_bounds__(256) featurize_ln_kernel(const float *__restri
                                                            int F, const int2 *__restrict__ pairs, int do_ln,
                                                            float eps2, float *__restrict__ out, int64_t ldo,
                                                            int Dp, int Fp, __nv_bfloat16 *__restrict__ out_hi,
-                                                           __nv_bfloat16 *__restrict__ out_lo) {
+                                                           __nv_bfloat16 *__restrict__ out_lo, int fmt) {
   extern __shared__ float sm[];
   const int warps = blockDim.x >> 5;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,9 +72,15 @@ __global__ void __launch_bounds__(256) featurize_ln_kernel(const float *__restri
       __nv_bfloat16 *oh = out_hi + m * ldo, *ol = out_lo + m * ldo;
       for (int f = lane; f < (int)ldo; f += 32) {
         const float v = f < F ? (sf[f] - mu) * rstd : (f == F ? 1.f : 0.f);  // column F = 1: bias column
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        oh[f] = h;
-        ol[f] = __float2bfloat16_rn(v - __bfloat162float(h));
+        if (fmt) {  // fp16 pairs (2-MMA inference forward)
+          const __half h = __float2half_rn(v);
+          reinterpret_cast<__half *>(oh)[f] = h;
+          reinterpret_cast<__half *>(ol)[f] = __float2half_rn(v - __half2float(h));
+        } else {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          oh[f] = h;
+          ol[f] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
       }
     } else {
       float *o = out + m * ldo;
@@ -97,7 +105,7 @@ __global__ void __launch_bounds__(256, (NF <= 20 ? 3 : 2)) featurize_reg_kernel(
                                                             int F, const int2 *__restrict__ pairs, int do_ln,
                                                             float eps2, float *__restrict__ out, int64_t ldo,
                                                             int atoms_pad, __nv_bfloat16 *__restrict__ out_hi,
-                                                            __nv_bfloat16 *__restrict__ out_lo) {
+                                                            __nv_bfloat16 *__restrict__ out_lo, int fmt) {
   extern __shared__ float4 sm4[];
   const int warps = blockDim.x >> 5;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,12 +204,19 @@ __global__ void __launch_bounds__(256, (NF <= 20 ? 3 : 2)) featurize_reg_kernel(
           // column F carries the constant 1 that turns the weight-gradient GEMM into [x_hat, 1]^T * delta
           const float x0 = f < F ? fmaf(v[t], scale, shift) : (f == F ? 1.f : 0.f);
           const float x1 = f + 1 < F ? fmaf(v[t + 1], scale, shift) : (f + 1 == F ? 1.f : 0.f);
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-          const uint32_t hw = *reinterpret_cast<const uint32_t *>(&h2);
-          const __nv_bfloat162 l2 =
-              __floats2bfloat162_rn(x0 - __uint_as_float(hw << 16), x1 - __uint_as_float(hw & 0xFFFF0000u));
-          *reinterpret_cast<__nv_bfloat162 *>(oh + 64 * (t >> 1)) = h2;
-          *reinterpret_cast<__nv_bfloat162 *>(ol + 64 * (t >> 1)) = l2;
+          if (fmt) {  // fp16 pairs
+            const __half2 h2 = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h2);
+            *reinterpret_cast<__half2 *>(oh + 64 * (t >> 1)) = h2;
+            *reinterpret_cast<__half2 *>(ol + 64 * (t >> 1)) = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+          } else {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+            const uint32_t hw = *reinterpret_cast<const uint32_t *>(&h2);
+            const __nv_bfloat162 l2 =
+                __floats2bfloat162_rn(x0 - __uint_as_float(hw << 16), x1 - __uint_as_float(hw & 0xFFFF0000u));
+            *reinterpret_cast<__nv_bfloat162 *>(oh + 64 * (t >> 1)) = h2;
+            *reinterpret_cast<__nv_bfloat162 *>(ol + 64 * (t >> 1)) = l2;
+          }
         }
       }
     } else {
@@ -226,7 +241,7 @@ static void launch_reg(Ctx &c, const float *coords, const int64_t *gather, int64
   const float eps = c.cfg.ln_eps;
   featurize_reg_kernel<NF, SPLIT><<<grid, warps * 32, smem, c.stream>>>(
       coords, gather, M, D, F, pairs ? c.pairs.p : nullptr, do_ln ? 1 : 0, eps * eps, out, ldo, atoms_pad, out_hi,
-      out_lo);
+      out_lo, c.split_fmt);
 }
 
 // Pullback of featurizer + LayerNorm (reference: sqpairdist_bwd_kernel! and its rrule,
@@ -394,7 +409,7 @@ static void launch_featurize_impl(Ctx &c, const float *coords, const int64_t *ga
   c.timer.begin(KC_FEATURIZE, c.stream);
   featurize_ln_kernel<<<grid, warps * 32, smem, c.stream>>>(coords, gather ? gather + gather_off : nullptr, M, D, F,
                                                             pairs ? c.pairs.p : nullptr, do_ln ? 1 : 0, eps * eps,
-                                                            out, ldo, Dp, Fp, out_hi, out_lo);
+                                                            out, ldo, Dp, Fp, out_hi, out_lo, c.split_fmt);
   c.timer.end(c.stream);
   IK_CUDA(cudaGetLastError());
   c.count_launch(KC_FEATURIZE, 4.0 * (double)(D + F) * (double)M);
@@ -406,7 +421,12 @@ void launch_featurize(Ctx &c, const float *coords, const int64_t *gather, int64_
 }
 
 void launch_featurize_split(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M,
-                            bool pairs, bool do_ln, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld) {
+                            bool pairs, bool do_ln, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld, int fmt) {
+  struct Reset {
+    int &f;
+    ~Reset() { f = 0; }
+  } reset{c.split_fmt};
+  c.split_fmt = fmt;  // read by the kernel launchers below
   launch_featurize_impl(c, coords, gather, gather_off, M, pairs, do_ln, nullptr, ld, out_hi, out_lo);
 }
 

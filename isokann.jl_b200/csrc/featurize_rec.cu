@@ -18,6 +18,8 @@
 //           rotation -> conflict-free), normalise, split into bf16 (hi, lo) and write 16-byte pieces that
 //           cover whole 128-byte lines of the row-major x_hat rows (or plain fp32 rows for isokann_featurize).
 // No distance is computed twice and no value leaves the SM before it is final.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ik {
@@ -96,11 +98,19 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t &h, uint32_t
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(r1), "f"(r0));
 }
 
+// fp16 pairs (2-MMA inference forward): hi = rn_f16(x), lo = rn_f16(x - hi)
+__device__ __forceinline__ void split2h(float x0, float x1, uint32_t &h, uint32_t &l) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&h));
+  const float r0 = x0 - hf.x, r1 = x1 - hf.y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(r1), "f"(r0));
+}
+
 template <bool SPLIT, bool HASMAP>
 __global__ void __launch_bounds__(256, 2)
     featurize_blk_kernel(const float *__restrict__ coords, const int64_t *__restrict__ gather, int64_t M, int D, int A,
                          const int *__restrict__ cmap, int F, int do_ln, float eps2, float *__restrict__ out,
-                         __nv_bfloat16 *__restrict__ out_hi, __nv_bfloat16 *__restrict__ out_lo, int64_t ldo) {
+                         __nv_bfloat16 *__restrict__ out_hi, __nv_bfloat16 *__restrict__ out_lo, int64_t ldo, int fmt) {
   extern __shared__ __align__(16) float smem_f[];
   const int W = blockDim.x >> 5;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -223,10 +233,17 @@ __global__ void __launch_bounds__(256, 2)
             for (int k = 0; k < 8; ++k) v[k] = f0 + k < F ? v[k] : (f0 + k == F ? 1.f : 0.f);
           }
           uint4 h, l;
-          split2(v[0], v[1], h.x, l.x);
-          split2(v[2], v[3], h.y, l.y);
-          split2(v[4], v[5], h.z, l.z);
-          split2(v[6], v[7], h.w, l.w);
+          if (fmt) {
+            split2h(v[0], v[1], h.x, l.x);
+            split2h(v[2], v[3], h.y, l.y);
+            split2h(v[4], v[5], h.z, l.z);
+            split2h(v[6], v[7], h.w, l.w);
+          } else {
+            split2(v[0], v[1], h.x, l.x);
+            split2(v[2], v[3], h.y, l.y);
+            split2(v[4], v[5], h.z, l.z);
+            split2(v[6], v[7], h.w, l.w);
+          }
           *reinterpret_cast<uint4 *>(ph) = h;
           *reinterpret_cast<uint4 *>(pl) = l;
         };
@@ -303,7 +320,7 @@ void launch_featurize_rec(Ctx &c, const float *coords, const int64_t *gather, in
     if (c.attr_needed(Ctx::ATTR_FEAT_BLK0 + id))
       IK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     kernel<<<grid, p.warps * 32, p.smem, c.stream>>>(coords, gather, M, c.D, A, c.tri_cmap.p, A * (A - 1) / 2,
-                                                     do_ln ? 1 : 0, eps * eps, out, out_hi, out_lo, ld);
+                                                     do_ln ? 1 : 0, eps * eps, out, out_hi, out_lo, ld, c.split_fmt);
   };
   const bool map = c.tri_cmap.p != nullptr;
   if (out_hi) {

@@ -26,6 +26,8 @@ struct TcGemm {
   int M, N, K;
   int mn_major;                       // 1: A is [K x M] and B is [K x N] in memory (M / N contiguous): weight gradients
   int ones_col;                       // split epilogues: write 1.0 into column N (bias column of the next wgrad)
+  int fmt;                            // 0: operands are bf16 (hi, lo); 1: fp16 (hi, lo) -- split outputs use the same format
+  int nmma;                           // 3 (default): hi*hi + hi*lo + lo*hi; 2: hi*hi + lo*hi (B rounded once; b_lo unused)
   int epi, act;
   const float *bias;                  // TC_EPI_BIAS_ACT_SPLIT
   __nv_bfloat16 *out_hi, *out_lo;     // split outputs
@@ -67,6 +69,7 @@ struct TcState {
   std::vector<SplitBuf> wF;    // forward operand of layer l (l = 0..L-2): [w_{l+1} x wp_l]
   std::vector<SplitBuf> wD;    // dgrad operand of layer l   (l = 1..L-2): [w_l x wp_{l+1}]
   std::vector<SplitBuf> wF_alt, wD_alt;  // second operand set: refreshed on the communication stream, then swapped in
+  std::vector<DevBuf<__nv_bfloat16>> wF16;  // fp16 copy of the forward operand (inference forward with 2 MMAs)
   SplitBuf delta[2];           // row-major delta ping-pong
   SplitBuf x_alt;              // second x_hat buffer: the featurizer of chunk i+1 overlaps the GEMMs of chunk i
   cudaStream_t feat_stream = nullptr;
@@ -78,8 +81,13 @@ struct TcState {
 };
 
 // featurizer + LayerNorm writing the split-bf16 A operand [M x ld] (pad columns zeroed)
+// fmt: 0 bf16 pairs, 1 fp16 pairs (same 16-bit buffers)
 void launch_featurize_split(Ctx &c, const float *coords, const int64_t *gather, int64_t gather_off, int64_t M,
-                            bool pairs, bool do_ln, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld);  // column F := 1
+                            bool pairs, bool do_ln, __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, int64_t ld,
+                            int fmt = 0);  // column F := 1
+// forward operand of a Dense layer rounded once to fp16: Wf16[out x ld_f] (K = in contiguous), for the 2-MMA
+// inference forward
+void launch_prep_weights_f16(Ctx &c, const float *seg, int fin, int fout, __nv_bfloat16 *wf16, int64_t ld_f);
 // fp32 [rows x cols] (dense) -> split bf16 [rows x ld], pad columns zeroed
 void launch_f32_to_split(Ctx &c, const float *in, int64_t rows, int cols, __nv_bfloat16 *hi, __nv_bfloat16 *lo,
                          int64_t ld);

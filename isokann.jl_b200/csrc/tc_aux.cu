@@ -1,6 +1,8 @@
 // Kernels around the tcgen05 GEMM: operand preparation (fp32 -> bf16 hi/lo split, weight layouts)
 // and the thin last Dense layer (out = d <= 8), which is a memory-bound row reduction rather
 // than a GEMM.  All of them are HBM-bound passes with 16-byte vector accesses.
+#include <cuda_fp16.h>
+
 #include "tc.cuh"
 
 namespace ik {
@@ -63,6 +65,23 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const float *__restri
       wf_hi[(int64_t)j * ld_f + i] = h;
       wf_lo[(int64_t)j * ld_f + i] = l;
     }
+  }
+}
+
+// ---- weights: fp32 [fin x fout] -> Wf16 [fout x ld_f] (transposed), each weight rounded once to fp16 ----
+__global__ void __launch_bounds__(256) prep_weights_f16_kernel(const float *__restrict__ seg, int fin, int fout,
+                                                               __half *__restrict__ wf, int64_t ld_f) {
+  __shared__ float t[64][65];
+  const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int r = ty; r < 64; r += 4) {
+    const int i = i0 + r, j = j0 + tx;
+    t[r][tx] = (i < fin && j < fout) ? seg[(int64_t)i * fout + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 64; r += 4) {
+    const int j = j0 + r, i = i0 + tx;
+    if (j < fout && i < fin) wf[(int64_t)j * ld_f + i] = __float2half_rn(t[tx][r]);
   }
 }
 
@@ -377,6 +396,15 @@ void launch_prep_weights(Ctx &c, const float *seg, int fin, int fout, __nv_bfloa
   dim3 grid(cdiv(fin, 64), cdiv(fout, 64));
   c.timer.begin(KC_TRAIN_EW, c.stream);
   prep_weights_kernel<<<grid, 256, 0, c.stream>>>(seg, fin, fout, wf_hi, wf_lo, ld_f, wd_hi, wd_lo, ld_d);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_TRAIN_EW);
+}
+
+void launch_prep_weights_f16(Ctx &c, const float *seg, int fin, int fout, __nv_bfloat16 *wf16, int64_t ld_f) {
+  dim3 grid(cdiv(fin, 64), cdiv(fout, 64));
+  c.timer.begin(KC_TRAIN_EW, c.stream);
+  prep_weights_f16_kernel<<<grid, 256, 0, c.stream>>>(seg, fin, fout, reinterpret_cast<__half *>(wf16), ld_f);
   c.timer.end(c.stream);
   IK_CUDA(cudaGetLastError());
   c.count_launch(KC_TRAIN_EW);

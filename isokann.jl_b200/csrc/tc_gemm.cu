@@ -20,6 +20,7 @@
 // Out-of-range rows/columns/k are zero-filled by TMA; stores are predicated.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -158,6 +159,13 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hi, uin
   const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
   lo = *reinterpret_cast<const uint32_t *>(&l2);
 }
+// fp16 variant (inference forward, TcGemm::fmt == 1): 11 significant bits per term, 22 kept
+__device__ __forceinline__ void split_pair_h(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));  // low half = x0
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+  const float r0 = x0 - hf.x, r1 = x1 - hf.y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
@@ -165,6 +173,8 @@ struct TcParams {
   int M, N, K;          // D is M x N, reduction length K (elements)
   int m_tiles, n_tiles, splits, kb_per_split, num_kb;
   int epi, act, mn_major, ones_col;
+  int fmt;              // operand format: 0 bf16 (hi, lo), 1 fp16 (hi, lo)
+  int nmma;             // MMAs per k-slice: 3 = hi*hi + hi*lo + lo*hi; 2 = hi*hi + lo*hi (B rounded once, no B_lo tile)
   int st_v8;            // split outputs are 32-byte aligned with a 32-byte multiple pitch: 256-bit stores
   const float *bias;    // [N] or nullptr
   __nv_bfloat16 *out_hi, *out_lo;  // split outputs, row-major, leading dimension ldo
@@ -316,8 +326,13 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint32_t tmem_a
         if (col0 + j >= p.N) v[j] = (p.ones_col && col0 + j == p.N) ? 1.f : 0.f;
     }
     uint32_t ph[16], pl[16];
+    if (p.fmt) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+      for (int j = 0; j < 16; ++j) split_pair_h(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+    }
     __nv_bfloat16 *dh = p.out_hi + row * p.ldo + col0;
     __nv_bfloat16 *dl = p.out_lo + row * p.ldo + col0;
     if (p.st_v8) {
@@ -441,12 +456,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES;
           const uint32_t full = bar_full + 8 * stage;
-          mbar_arrive_expect_tx(full, STAGE_BYTES);
+          mbar_arrive_expect_tx(full, p.nmma == 2 ? STAGE_BYTES - B_TILE : STAGE_BYTES);
           if (!p.mn_major) {
             tma_load_2d(sa, &map_ah, full, kb * BK, mb * BM);
             tma_load_2d(sa + A_TILE, &map_al, full, kb * BK, mb * BM);
             tma_load_2d(sa + 2 * A_TILE, &map_bh, full, kb * BK, nb * BN);
-            tma_load_2d(sa + 2 * A_TILE + B_TILE, &map_bl, full, kb * BK, nb * BN);
+            if (p.nmma != 2) tma_load_2d(sa + 2 * A_TILE + B_TILE, &map_bl, full, kb * BK, nb * BN);
           } else {  // boxes of 64 (M or N, contiguous) x 64 (k)
 #pragma unroll
             for (int b = 0; b < BM / 64; ++b) {
@@ -470,7 +485,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128
-      uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // (format fields: 1 = bf16, 0 = fp16)
+      const uint32_t fbits = p.fmt ? 0u : ((1u << 7) | (1u << 10));
+      uint32_t idesc = (1u << 4) | fbits | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       if (p.mn_major) idesc |= (1u << 15) | (1u << 16);  // A and B are MN-major
       uint32_t stage = 0, phase = 0;
       int it = 0;
@@ -498,7 +515,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
             // K-major: 16 bf16 = 32 B inside the swizzle atom; MN-major: 16 k rows = two 1024 B groups
             const uint64_t adv = mn ? (uint64_t)((k * 2048) >> 4) : (uint64_t)((k * 32) >> 4);
             umma_f16(tmem_d, dah + adv, dbh + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            umma_f16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+            if (p.nmma != 2) umma_f16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
             umma_f16(tmem_d, dal + adv, dbh + adv, idesc, 1u);
           }
           umma_commit(bar_empty + 8 * stage);  // smem stage reusable once these MMAs retire
@@ -653,11 +670,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
           const uint32_t sa = base + stage * STAGE2_BYTES;
           const uint32_t full_local = bar_full + 8 * stage;
           const uint32_t full_leader = full_local & 0xFEFFFFFFu;  // peer bit cleared: the even CTA of the pair
-          if (leader) mbar_arrive_expect_tx(full_local, 2 * STAGE2_BYTES);
+          if (leader) mbar_arrive_expect_tx(full_local, 2 * (p.nmma == 2 ? STAGE2_BYTES - B2_TILE : STAGE2_BYTES));
           tma_load_2d_cg2(sa, &map_ah, full_leader, kb * BK, m0);
           tma_load_2d_cg2(sa + A_TILE, &map_al, full_leader, kb * BK, m0);
           tma_load_2d_cg2(sa + 2 * A_TILE, &map_bh, full_leader, kb * BK, n0);
-          tma_load_2d_cg2(sa + 2 * A_TILE + B2_TILE, &map_bl, full_leader, kb * BK, n0);
+          if (p.nmma != 2) tma_load_2d_cg2(sa + 2 * A_TILE + B2_TILE, &map_bl, full_leader, kb * BK, n0);
           if (++stage == STAGES2) {
             stage = 0;
             phase ^= 1;
@@ -669,7 +686,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
       // D=f32, A=B=bf16, K-major, N=256, M=256 (2 x 128 across the CTA pair)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      const uint32_t fbits = p.fmt ? 0u : ((1u << 7) | (1u << 10));  // 1 = bf16, 0 = fp16
+      const uint32_t idesc = (1u << 4) | fbits | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int t = cl; t < total_tiles; t += ncl, ++it) {
@@ -688,7 +706,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adv = (uint64_t)((k * 32) >> 4);
             umma2_f16(tmem_d, dah + adv, dbh + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma2_f16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+            if (p.nmma != 2) umma2_f16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
             umma2_f16(tmem_d, dal + adv, dbh + adv, idesc, 1u);
           }
           umma_commit_mc(bar_empty + 8 * stage);
@@ -808,6 +826,7 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   p.kb_per_split = cdiv(p.num_kb, splits);
   p.splits = cdiv(p.num_kb, p.kb_per_split);
   p.epi = g.epi; p.act = g.act; p.mn_major = g.mn_major; p.ones_col = g.ones_col;
+  p.fmt = g.fmt; p.nmma = g.nmma == 2 ? 2 : 3;
   p.bias = g.bias;
   p.out_hi = g.out_hi; p.out_lo = g.out_lo; p.ldo = g.ldo;
   p.out_f32 = g.out_f32; p.ldc = g.ldc;
@@ -860,6 +879,7 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
     c.timer.end(c.stream);
     IK_CUDA(cudaGetLastError());
     c.count_launch(KC_GEMM, 2.0 * (double)g.M * (double)g.N * (double)g.K);
+    if (c.timer.enabled) c.stats.gemm_mma_flops += 2.0 * p.nmma * (double)g.M * (double)g.N * (double)g.K;
     return 1;
   }
   const int total = p.m_tiles * p.n_tiles * p.splits;
@@ -885,6 +905,7 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   c.timer.end(c.stream);
   IK_CUDA(cudaGetLastError());
   c.count_launch(KC_GEMM, 2.0 * (double)g.M * (double)g.N * (double)g.K);
+  if (c.timer.enabled) c.stats.gemm_mma_flops += 2.0 * p.nmma * (double)g.M * (double)g.N * (double)g.K;
   return p.splits;
 }
 

@@ -57,7 +57,7 @@ class Stats(C.Structure):
         ("ms_koopman_total", C.c_double), ("ms_target_total", C.c_double), ("ms_train_total", C.c_double),
         ("n_gemm_launches", C.c_int64), ("n_featurize_launches", C.c_int64),
         ("gemm_flops", C.c_double), ("featurize_bytes", C.c_double), ("ms_nccl", C.c_double),
-        ("graph_launches", C.c_int64), ("p2p_exchanges", C.c_int64),
+        ("graph_launches", C.c_int64), ("gemm_mma_flops", C.c_double), ("p2p_exchanges", C.c_int64),
     ]
 
     def as_dict(self):

@@ -90,6 +90,37 @@ def test_tc_nd_target_iteration(pkg, oracle, target, topts):
     assert np.allclose(r["chi_lib"], r["chi_ref"], rtol=2e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("widths,target", [([231, 256, 320, 1], "shiftscale"), ([231, 512, 264, 3], "isa"),
+                                           ([231, 300, 1], "shiftscale")])
+def test_fp16x2_inference_forward(pkg, oracle, monkeypatch, widths, target):
+    """ISOKANN_TC_FWD=fp16x2: the inference forward (chis, Koopman pass) with fp16 (hi, lo) activations, weights
+    rounded once to fp16 and two MMAs per product, against the oracle and the default bf16 x 3 path; then three
+    iterations (the training steps stay bf16 x 3, only their targets come from the fp16 forward)"""
+    w = wide(pkg, widths)
+    N, K = 1300, 3
+    xs, ys = pkg.synthetic.make_data(w, N, K)
+    om = oracle_model(oracle, w.widths, True, 5)
+    rng = np.random.default_rng(9)
+    om.ln_scale = rng.uniform(0.5, 1.5, w.F).astype(np.float32)
+    om.ln_bias = (0.1 * rng.normal(size=w.F)).astype(np.float32)
+    om.b = [(0.1 * rng.normal(size=b.shape)).astype(np.float32) for b in om.b]
+    flat = oracle.flatten_params(om)
+    ref = make_iso(pkg, w, xs, ys, flat, opt="adam", target=target, minibatch=400, gemm="tc")
+    monkeypatch.setenv("ISOKANN_TC_FWD", "fp16x2")
+    h2 = make_iso(pkg, w, xs, ys, flat, opt="adam", target=target, minibatch=400, gemm="tc")
+    xsf, ysf = oracle_features(oracle, w, xs, ys)
+    chi_ref, k_ref = oracle.forward(om, xsf), oracle.expectation(om, ysf)
+    c2, k2 = records(pkg.chis(h2)), records(pkg.koopman(h2))
+    assert np.allclose(c2, chi_ref, rtol=TOL_CHI, atol=1e-4), np.abs(c2 - chi_ref).max()
+    assert np.allclose(k2, k_ref, rtol=TOL_CHI, atol=1e-4), np.abs(k2 - k_ref).max()
+    assert np.abs(c2 - records(pkg.chis(ref))).max() < 1.5e-4
+    perms = pkg.synthetic.make_perms(w, N, 3)
+    pkg.run_(h2, 3, perms=perms)
+    pkg.run_(ref, 3, perms=perms)
+    assert np.allclose(h2.losses, ref.losses, rtol=5e-3), (h2.losses, ref.losses)
+    assert np.abs(pkg.chis(h2) - pkg.chis(ref)).max() < 2e-3
+
+
 def test_tc_mode_rejects_narrow_nets(pkg):
     model = pkg.pairnet(n=231)
     with pytest.raises(pkg.IsokannError):
