@@ -1300,6 +1300,33 @@ void capture_epoch(Ctx &c, Steps &&steps, int64_t N, int64_t bs, int64_t nb, boo
   g.alloc_gen = gen;
 }
 
+// the indices feed device gathers (coords + idx*D, target[idx]): reject anything outside 1..N before the upload
+void validate_perm(const int64_t *perm_host, int64_t N) {
+  IK_REQUIRE(perm_host != nullptr, ISOKANN_BAD_ARGUMENT, "perm must not be NULL");
+  int64_t lo = INT64_MAX, hi = INT64_MIN;
+  for (int64_t i = 0; i < N; ++i) {
+    lo = std::min(lo, perm_host[i]);
+    hi = std::max(hi, perm_host[i]);
+  }
+  IK_REQUIRE(lo >= 1 && hi <= N, ISOKANN_BAD_ARGUMENT,
+             "perm must hold 1-based indices in 1..N (got " + std::to_string(lo) + ".." + std::to_string(hi) + ")");
+}
+
+// isokann_iterate knows the permutation of the coming epoch before the Koopman pass starts: its upload (8 bytes per
+// start point, from pageable caller memory) runs on the copy stream beside that pass instead of between the target
+// and the first optimiser step
+void preload_perm(Ctx &c, const int64_t *perm_host) {
+  validate_perm(perm_host, c.N);
+  if (!c.copy_stream) IK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  if (!c.perm_event) IK_CUDA(cudaEventCreateWithFlags(&c.perm_event, cudaEventDisableTiming));
+  c.perm_raw.ensure((size_t)c.N);
+  c.perm_dev.ensure((size_t)c.N);
+  IK_CUDA(cudaMemcpyAsync(c.perm_raw.p, perm_host, (size_t)c.N * sizeof(int64_t), cudaMemcpyHostToDevice,
+                          c.copy_stream));
+  IK_CUDA(cudaEventRecord(c.perm_event, c.copy_stream));
+  c.perm_preloaded = perm_host;
+}
+
 double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool partial) {
   IK_REQUIRE(c.xs != nullptr, ISOKANN_ERR_STATE, "no data: call isokann_set_data first");
   IK_REQUIRE(c.has_target, ISOKANN_ERR_STATE, "no target: call isokann_target / isokann_set_target first");
@@ -1307,21 +1334,18 @@ double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool par
   IK_REQUIRE(perm_host != nullptr, ISOKANN_BAD_ARGUMENT, "perm must not be NULL");
   IK_REQUIRE(minibatch >= 0, ISOKANN_BAD_ARGUMENT, "minibatch must be >= 0");
   const int64_t N = c.N;
-  {  // the indices feed device gathers (coords + idx*D, target[idx]): reject anything outside 1..N before the upload
-    int64_t lo = INT64_MAX, hi = INT64_MIN;
-    for (int64_t i = 0; i < N; ++i) {
-      lo = std::min(lo, perm_host[i]);
-      hi = std::max(hi, perm_host[i]);
-    }
-    IK_REQUIRE(lo >= 1 && hi <= N, ISOKANN_BAD_ARGUMENT,
-               "perm must hold 1-based indices in 1..N (got " + std::to_string(lo) + ".." + std::to_string(hi) + ")");
-  }
+  const bool preloaded = c.perm_preloaded == perm_host;
+  c.perm_preloaded = nullptr;
+  if (!preloaded) validate_perm(perm_host, N);
   const int64_t bs = (minibatch == 0 || N < minibatch) ? N : minibatch;  // src/iso.jl:180
   const int64_t nb = partial ? (N + bs - 1) / bs : N / bs;               // partial=false drops the tail
   c.timer.begin(KC_PHASE_TRAIN, c.stream);
   c.perm_raw.ensure((size_t)N);
   c.perm_dev.ensure((size_t)N);
-  IK_CUDA(cudaMemcpyAsync(c.perm_raw.p, perm_host, (size_t)N * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+  if (preloaded)
+    IK_CUDA(cudaStreamWaitEvent(c.stream, c.perm_event, 0));
+  else
+    IK_CUDA(cudaMemcpyAsync(c.perm_raw.p, perm_host, (size_t)N * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
   launch_perm_to_zero_based(c, c.perm_raw.p, N, c.perm_dev.p);
   IK_CUDA(cudaMemsetAsync(c.epoch_loss.p, 0, sizeof(double), c.stream));
   {
@@ -1782,6 +1806,7 @@ int32_t isokann_destroy(isokann_ctx *c) {
   }
   for (auto e : c->ys_events) cudaEventDestroy(e);
   if (c->xs_event) cudaEventDestroy(c->xs_event);
+  if (c->perm_event) cudaEventDestroy(c->perm_event);
   release_host_registrations(*c);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -2299,6 +2324,8 @@ int32_t isokann_iterate(isokann_ctx *c, int32_t transform, const isokann_target_
     IK_REQUIRE(perms != nullptr, ISOKANN_BAD_ARGUMENT, "perms must not be NULL");
     int64_t k = 0;
     for (int64_t it = 0; it < n_iter; ++it) {
+      IK_REQUIRE(c->xs != nullptr, ISOKANN_ERR_STATE, "no data: call isokann_set_data first");
+      preload_perm(*c, perms + k * c->N);
       compute_target(*c, transform, opts);
       for (int64_t e = 0; e < epochs; ++e, ++k) {
         const double l = train_epoch(*c, perms + k * c->N, minibatch, false);

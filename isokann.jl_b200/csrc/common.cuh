@@ -236,6 +236,8 @@ struct Ctx {
   std::vector<cudaEvent_t> ys_events;
   int64_t ys_chunk_pts = 0;   // start points per upload chunk; 0 = no pending upload
   int64_t ys_chunks_pending = 0;
+  cudaEvent_t perm_event = nullptr;            // the coming epoch's permutation is on its way (preload_perm)
+  const int64_t *perm_preloaded = nullptr;     // caller pointer whose contents perm_raw holds / will hold
   cudaEvent_t xs_event = nullptr;  // xs rides the copy stream behind ys (only the training side reads it)
   // cudaFuncSetAttribute is per device: remembered per context, not per process (one process may hold contexts
   // on several devices)

@@ -93,9 +93,11 @@ def test_tc_nd_target_iteration(pkg, oracle, target, topts):
 @pytest.mark.parametrize("widths,target", [([231, 256, 320, 1], "shiftscale"), ([231, 512, 264, 3], "isa"),
                                            ([231, 300, 1], "shiftscale")])
 def test_fp16x2_inference_forward(pkg, oracle, monkeypatch, widths, target):
-    """ISOKANN_TC_FWD=fp16x2: the inference forward (chis, Koopman pass) with fp16 (hi, lo) activations, weights
-    rounded once to fp16 and two MMAs per product, against the oracle and the default bf16 x 3 path; then three
-    iterations (the training steps stay bf16 x 3, only their targets come from the fp16 forward)"""
+    """ISOKANN_TC_FWD=fp16x2 (opt-in): the inference forward (chis, Koopman pass) with fp16 (hi, lo) activations,
+    weights rounded once to fp16 and two MMAs per product, against the oracle and the default bf16 x 3 path; then
+    three iterations (the training steps stay bf16 x 3, only their targets come from the fp16 forward).
+    Rounding every weight once to 11 bits costs ~2e-4 relative on chi (measured: profiles/r02_split_accuracy_gpu.md),
+    which is why this mode is not the default: the tolerances below are 3-4x the default path's."""
     w = wide(pkg, widths)
     N, K = 1300, 3
     xs, ys = pkg.synthetic.make_data(w, N, K)
@@ -111,14 +113,14 @@ def test_fp16x2_inference_forward(pkg, oracle, monkeypatch, widths, target):
     xsf, ysf = oracle_features(oracle, w, xs, ys)
     chi_ref, k_ref = oracle.forward(om, xsf), oracle.expectation(om, ysf)
     c2, k2 = records(pkg.chis(h2)), records(pkg.koopman(h2))
-    assert np.allclose(c2, chi_ref, rtol=TOL_CHI, atol=1e-4), np.abs(c2 - chi_ref).max()
-    assert np.allclose(k2, k_ref, rtol=TOL_CHI, atol=1e-4), np.abs(k2 - k_ref).max()
-    assert np.abs(c2 - records(pkg.chis(ref))).max() < 1.5e-4
+    assert np.allclose(c2, chi_ref, rtol=3e-4, atol=1e-4), np.abs(c2 - chi_ref).max()
+    assert np.allclose(k2, k_ref, rtol=3e-4, atol=1e-4), np.abs(k2 - k_ref).max()
+    assert np.abs(c2 - records(pkg.chis(ref))).max() < 3e-4 * max(1.0, np.abs(chi_ref).max())
     perms = pkg.synthetic.make_perms(w, N, 3)
     pkg.run_(h2, 3, perms=perms)
     pkg.run_(ref, 3, perms=perms)
-    assert np.allclose(h2.losses, ref.losses, rtol=5e-3), (h2.losses, ref.losses)
-    assert np.abs(pkg.chis(h2) - pkg.chis(ref)).max() < 2e-3
+    assert np.allclose(h2.losses, ref.losses, rtol=2e-2), (h2.losses, ref.losses)
+    assert np.abs(pkg.chis(h2) - pkg.chis(ref)).max() < 5e-3
 
 
 def test_tc_mode_rejects_narrow_nets(pkg):
