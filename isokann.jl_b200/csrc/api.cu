@@ -310,7 +310,6 @@ void forward_rows_tcn(Ctx &c, const float *in, const int64_t *gather, int64_t go
   tc_ensure_rows(c, M);
   ensure_tc_weights(c);
   const bool pairs = in_is_coords && c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
-  launch_featurize_split(c, in, gather, goff, M, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0]);
   const int fin = c.cfg.widths[0], fout = c.cfg.widths[1];
   TcGemm g{};
   g.a_hi = t.act[0].hi.p; g.a_lo = t.act[0].lo.p; g.lda = t.wp[0];
@@ -326,6 +325,9 @@ void forward_rows_tcn(Ctx &c, const float *in, const int64_t *gather, int64_t go
   for (int l = 1; l < c.L; ++l) g.tail.seg[l - 1] = c.params.p + c.off_w[l];
   g.chi_out = c.act[c.L].p;
   g.splits = 1;
+  // coordinates straight into the tensor-core kernel: x_hat never reaches HBM
+  if (pairs && gather == nullptr && launch_koop_fused(c, in, M, c.ln, g)) return;
+  launch_featurize_split(c, in, gather, goff, M, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0]);
   launch_tc_gemm(c, g);
 }
 
@@ -1701,6 +1703,7 @@ int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out) {
     c->tc_no_pair = getenv("ISOKANN_TC_NO_PAIR") != nullptr;
     c->tc_no_head = getenv("ISOKANN_TC_NO_HEAD") != nullptr;
     { const char *e = getenv("ISOKANN_FEAT_REC"); c->feat_rec_off = e && e[0] == '0'; }
+    { const char *e = getenv("ISOKANN_KOOP_FUSED"); c->koop_fused_off = e && e[0] == '0'; }
     c->tc_no_overlap = getenv("ISOKANN_OVERLAP") == nullptr;  // opt-in: measured +0.6 % under the 1 kW cap
     if (c->tc || c->tcn) {
       c->tcs = new TcState;
@@ -1783,6 +1786,7 @@ int32_t isokann_destroy(isokann_ctx *c) {
     delete c->tcs;
   }
   c->tri_cmap.release();
+  c->koop_start16.release();
   c->pairs.release();
   c->adj_off.release();
   c->adj.release();

@@ -214,6 +214,8 @@ struct Ctx {
   bool wf16_valid = false;    // tcs->wF16 matches the current parameters
   int tri_n = 0;            // atoms of an upper-triangle featurizer (all pairs / atom subset), else 0
   DevBuf<int> tri_cmap;     // atom subset: coordinate c of the selection -> coordinate of the record (else null)
+  DevBuf<short2> koop_start16;  // fused narrow forward: (i, j) of every 16th feature of the upper triangle
+  bool koop_fused_off = false;  // ISOKANN_KOOP_FUSED=0: materialise x_hat and run featurizer + GEMM separately (A/B)
   bool feat_rec_off = false;  // ISOKANN_FEAT_REC=0: keep the lane = feature kernel (A/B comparison)
   bool tc_no_overlap = false; // unless ISOKANN_OVERLAP=1: featurizer and GEMMs on one stream
   bool tc_no_head = false;     // ISOKANN_TC_NO_HEAD=1: separate thin_forward / loss_delta / thin_dgrad kernels (A/B)
@@ -241,7 +243,7 @@ struct Ctx {
   cudaEvent_t xs_event = nullptr;  // xs rides the copy stream behind ys (only the training side reads it)
   // cudaFuncSetAttribute is per device: remembered per context, not per process (one process may hold contexts
   // on several devices)
-  enum { ATTR_FEAT_BWD = 0, ATTR_FEAT_LN, ATTR_FEAT_BLK0, ATTR_NARROW = 6, ATTR_TC1, ATTR_TC2, ATTR_P2P };
+  enum { ATTR_FEAT_BWD = 0, ATTR_FEAT_LN, ATTR_FEAT_BLK0, ATTR_NARROW = 6, ATTR_TC1, ATTR_TC2, ATTR_P2P, ATTR_KOOPF };
   uint32_t func_attr_done = 0;
   bool attr_needed(int bit) {
     if (func_attr_done >> bit & 1u) return false;

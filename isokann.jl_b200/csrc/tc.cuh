@@ -45,6 +45,8 @@ struct TcGemm {
 };
 
 int launch_tc_gemm(Ctx &c, const TcGemm &g);  // returns the number of split-K slices written
+// narrow nets: featurizer + LayerNorm + first layer + tail in one kernel, from coordinate records (tc_gemm.cu)
+bool launch_koop_fused(Ctx &c, const float *coords, int64_t M, bool do_ln, const TcGemm &g);
 
 // a split-bf16 matrix: hi/lo planes, rows x ld
 struct SplitBuf {

@@ -748,6 +748,284 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fused narrow-net forward: coordinates -> chi in ONE kernel (pairnet F -> h1 <= 128 -> <= 16 ... -> d).
+// Replaces flatpairdists + cached features + model(x) of the reference for the K*N-sample Koopman pass
+// (src/utils/pairdists.jl:6-24, src/simulation.jl:110-114, src/isotarget.jl:18): x_hat never exists in HBM, the
+// kernel reads 4*D bytes per sample and writes 4*d.
+//
+//   warps 0..15  producers.  A tile is 128 records; lane = record, the 4 warps of a record group split every k-block
+//                of 64 features in 16-feature quarters.  Coordinates are staged transposed ([coordinate][record]) by
+//                cp.async.  Pass 1 walks the strict upper triangle (column-major, halfinds order) once for the
+//                LayerNorm statistics (pivoted sums: sum(d - d0), sum((d - d0)^2), so no cancellation); pass 2 walks
+//                it again k-block by k-block, normalises, splits into bf16 (hi, lo) and stores 16-byte pieces
+//                straight into the 128B-swizzled K-major A stage that tcgen05.mma reads.  (Recomputing the distances
+//                costs ~12 instructions per feature; parking them would cost 84 KB per 32 villin records and cap the
+//                tile at 32 rows.)
+//   warp 16      MMA issuer: 3 MMAs per k-slice (hi*hi, hi*lo, lo*hi), M = 128, N = h1 rounded up to 16
+//   warp 17      TMA loads of the first layer's weights (hi, lo), one [N x 64] box pair per k-block
+//   warps 18..21 epilogue (warp % 4 = TMEM lane quarter): bias + activation + the remaining tiny layers per row
+//                (the TC_EPI_TAIL epilogue of the GEMM above), chi to global memory
+// A stages: 2 x 32 KiB, B stages: 2 x (2 * N * 128 B), accumulator double-buffered in TMEM.
+// ------------------------------------------------------------------------------------------
+constexpr int KF_PW = 16;                      // producer warps
+constexpr int KF_THREADS = 32 * (KF_PW + 6);   // + MMA, TMA, 4 epilogue warps
+constexpr int KF_ROWS = 128;
+constexpr int KF_CP = 129;                     // words per staged coordinate row (128 records + 1 pad)
+constexpr int KF_ASTAGE = 2 * KF_ROWS * 128;   // bytes: hi + lo tile of one k-block
+
+struct KoopFusedP {
+  const float *coords;       // [M][D] records
+  const int *cmap;           // atom subset: coordinate c of the selection -> coordinate of the record, or nullptr
+  int64_t M;
+  int D, A, F, C;            // record length, atoms in the triangle, features, staged coordinates (3A)
+  int nkb, nmma_n;           // k-blocks of 64 features, MMA N (multiple of 16, <= 128)
+  int do_ln;
+  float eps2;
+  const short2 *start16;     // (i, j) of feature 16*t for every t (column-major strict upper triangle)
+  TcParams ep;               // epilogue parameters (TC_EPI_TAIL)
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(KF_THREADS, 1)
+koop_fused_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, KoopFusedP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *base_ptr = smem_raw + (base - raw);
+  const int bstage = 2 * p.nmma_n * 128;                          // bytes of one B stage (hi + lo)
+  const int bstage_al = (bstage + 1023) & ~1023;
+  // layout: A stages | B stages | barriers | tail weights | stats | coordinates
+  const uint32_t a_off = 0, b_off = 2 * KF_ASTAGE, bar_off = b_off + 2 * bstage_al;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(base_ptr + bar_off);
+  const uint32_t bar_afull = smem_u32(bars), bar_aempty = bar_afull + 16, bar_bfull = bar_afull + 32,
+                 bar_bempty = bar_afull + 48, bar_tfull = bar_afull + 64, bar_tempty = bar_afull + 80;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
+  float *tailw = reinterpret_cast<float *>(base_ptr + bar_off + 128);
+  float2 *part = reinterpret_cast<float2 *>(tailw + TAIL_FLOATS);       // [4][128] partial (s1, s2) per quarter
+  float2 *stat = part + 4 * KF_ROWS;                                     // [128] (scale, shift)
+  float *coord = reinterpret_cast<float *>(stat + KF_ROWS);              // [C][KF_CP]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = (p.M + KF_ROWS - 1) / KF_ROWS;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_afull + 8 * s, KF_PW);
+      mbar_init(bar_aempty + 8 * s, 1);
+      mbar_init(bar_bfull + 8 * s, 1);
+      mbar_init(bar_bempty + 8 * s, 1);
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == KF_PW) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {  // tail layers' [W; b], rows padded to a multiple of 4 floats (same layout as tc_gemm_kernel<TC_EPI_TAIL>)
+    int off = 0;
+    for (int i = 0; i < p.ep.tail.nl; ++i) {
+      const int rows = p.ep.tail.w[i] + 1, cols = p.ep.tail.w[i + 1], cp = (cols + 3) & ~3;
+      for (int e = threadIdx.x; e < rows * cp; e += blockDim.x) {
+        const int r = e / cp, cc = e - r * cp;
+        tailw[off + e] = cc < cols ? __ldg(p.ep.tail.seg[i] + (int64_t)r * cols + cc) : 0.f;
+      }
+      off += rows * cp;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < KF_PW) {
+    // ===================== producers =====================
+    const int grp = warp & 3, qtr = warp >> 2;        // record group (32 records), 16-feature quarter of a k-block
+    const int rec = grp * 32 + lane;                  // row of the tile
+    const float *at = coord + rec;
+    const float invF = 1.0f / (float)p.F;
+    const uint32_t coord_s = smem_u32(coord);
+    uint32_t it = 0;                                  // k-blocks produced so far (stage = it & 1)
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int64_t m0 = t * KF_ROWS;
+      const int nvalid = (int)(p.M - m0 < KF_ROWS ? p.M - m0 : KF_ROWS);
+      // ---- stage the coordinates of the tile, transposed; rows past M repeat the last valid record
+      named_bar_sync(1, KF_PW * 32);  // everybody has finished reading the previous tile's coordinates
+      for (int r = warp; r < KF_ROWS; r += KF_PW) {
+        const int64_t m = m0 + (r < nvalid ? r : nvalid - 1);
+        const float *g = p.coords + m * p.D;
+        for (int c = lane; c < p.C; c += 32) {
+          const float *src = g + (p.cmap ? __ldg(p.cmap + c) : c);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(coord_s + 4u * (uint32_t)(c * KF_CP + r)), "l"(src)
+                       : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      named_bar_sync(1, KF_PW * 32);
+      // ---- the walk over this thread's features: 16 consecutive features of every k-block
+      // EMIT == false: LayerNorm sums only; true: normalise, split, store into the A stage
+      float scale = 1.f, shift = 0.f;
+      // pivot of the variance sums: the record's first distance
+      float piv;
+      {
+        const float dx = at[0] - at[3 * KF_CP], dy = at[KF_CP] - at[4 * KF_CP], dz = at[2 * KF_CP] - at[5 * KF_CP];
+        piv = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+      }
+      for (int pass = p.do_ln ? 0 : 1; pass < 2; ++pass) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          const int f0 = kb * 64 + qtr * 16;
+          uint32_t stage = 0, a_hi_s = 0;
+          if (pass == 1) {
+            stage = it & 1u;
+            mbar_wait(bar_aempty + 8 * stage, ((it >> 1) & 1u) ^ 1u);   // the MMAs that read this stage have retired
+            a_hi_s = base + a_off + stage * KF_ASTAGE;
+          }
+          float v[16];
+          if (f0 < p.F) {
+            const short2 st = __ldg(p.start16 + (f0 >> 4));
+            int i = st.x, j = st.y;
+            float cx = at[(3 * j) * KF_CP], cy = at[(3 * j + 1) * KF_CP], cz = at[(3 * j + 2) * KF_CP];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              float d = 0.f;
+              if (f0 + k < p.F) {
+                const float dx = at[(3 * i) * KF_CP] - cx, dy = at[(3 * i + 1) * KF_CP] - cy,
+                            dz = at[(3 * i + 2) * KF_CP] - cz;
+                const float sq = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(sq));
+                if (++i == j) {
+                  i = 0;
+                  ++j;
+                  if (j < p.A) {
+                    cx = at[(3 * j) * KF_CP];
+                    cy = at[(3 * j + 1) * KF_CP];
+                    cz = at[(3 * j + 2) * KF_CP];
+                  }
+                }
+                if (pass == 0) {
+                  const float e = d - piv;
+                  s1 += e;
+                  s2 = fmaf(e, e, s2);
+                }
+              }
+              v[k] = (pass == 1 && f0 + k < p.F) ? fmaf(d, scale, shift) : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = 0.f;
+          }
+          if (pass == 1) {
+            // row `rec` of the K-major, 128B-swizzled tile: 16-byte chunk c of the row sits at chunk c ^ (rec & 7)
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) split_pair(v[2 * k], v[2 * k + 1], h[k], l[k]);
+            const uint32_t row = a_hi_s + (uint32_t)rec * 128u;
+            const uint32_t c0 = (uint32_t)((2 * qtr) ^ (rec & 7)) << 4, c1 = (uint32_t)((2 * qtr + 1) ^ (rec & 7)) << 4;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c0), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c1), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + KF_ROWS * 128 + c0), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + KF_ROWS * 128 + c1), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_afull + 8 * stage);
+            ++it;
+          }
+        }
+        if (pass == 0) {
+          part[qtr * KF_ROWS + rec] = make_float2(s1, s2);
+          named_bar_sync(1, KF_PW * 32);
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 x = part[q * KF_ROWS + rec];
+            a += x.x;
+            b += x.y;
+          }
+          const float me = a * invF;                                  // mean of (d - pivot)
+          scale = rsqrtf(fmaxf(fmaf(-me, me, b * invF), 0.f) + p.eps2);
+          shift = -(piv + me) * scale;
+        }
+      }
+    }
+  } else if (warp == KF_PW) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nmma_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t it = 0;
+      int tl = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
+        const int acc = tl & 1;
+        mbar_wait(bar_tempty + 8 * acc, ((tl >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 128;
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const uint32_t stage = it & 1u, ph = (it >> 1) & 1u;
+          mbar_wait(bar_afull + 8 * stage, ph);
+          mbar_wait(bar_bfull + 8 * stage, ph);
+          tc_fence_after();
+          const uint32_t sa = base + a_off + stage * KF_ASTAGE, sb = base + b_off + stage * bstage_al;
+          const uint64_t dah = make_desc_sw128(sa), dal = make_desc_sw128(sa + KF_ROWS * 128);
+          const uint64_t dbh = make_desc_sw128(sb), dbl = make_desc_sw128(sb + p.nmma_n * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            umma_f16(tmem_d, dah + adv, dbh + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_f16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+            umma_f16(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+          }
+          umma_commit(bar_aempty + 8 * stage);
+          umma_commit(bar_bempty + 8 * stage);
+        }
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else if (warp == KF_PW + 1) {
+    // ===================== TMA: first-layer weights =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const uint32_t stage = it & 1u, ph = (it >> 1) & 1u;
+          mbar_wait(bar_bempty + 8 * stage, ph ^ 1u);
+          const uint32_t sb = base + b_off + stage * bstage_al, full = bar_bfull + 8 * stage;
+          mbar_arrive_expect_tx(full, (uint32_t)bstage);
+          tma_load_2d(sb, &map_bh, full, kb * BK, 0);
+          tma_load_2d(sb + p.nmma_n * 128, &map_bl, full, kb * BK, 0);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 18..21) =====================
+    const int quarter = warp & 3;
+    int tl = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
+      const int acc = tl & 1;
+      mbar_wait(bar_tfull + 8 * acc, (tl >> 1) & 1);
+      tc_fence_after();
+      epilogue_tile<TC_EPI_TAIL>(p.ep, tmem_base + acc * 128, t * KF_ROWS, 0, 0, quarter, 0, lane, tailw);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == KF_PW) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -907,6 +1185,59 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
   c.count_launch(KC_GEMM, 2.0 * (double)g.M * (double)g.N * (double)g.K);
   if (c.timer.enabled) c.stats.gemm_mma_flops += 2.0 * p.nmma * (double)g.M * (double)g.N * (double)g.K;
   return p.splits;
+}
+
+// coordinates -> chi for a narrow net in one kernel (see koop_fused_kernel).  g describes the first-layer GEMM exactly
+// like the TC_EPI_TAIL launch it replaces (b_hi/b_lo, ldb, N, K, bias, act, tail, chi_out); returns false if the
+// shapes do not fit, in which case the caller materialises x_hat and uses launch_tc_gemm.
+bool launch_koop_fused(Ctx &c, const float *coords, int64_t M, bool do_ln, const TcGemm &g) {
+  const int A = c.tri_n;
+  if (A < 2 || c.koop_fused_off || g.N > 128 || g.K != A * (A - 1) / 2 || g.K < 64 || M <= 0) return false;
+  const int F = g.K, C = 3 * A;
+  const int nmma_n = (g.N + 15) & ~15;
+  const int bstage_al = (2 * nmma_n * 128 + 1023) & ~1023;
+  const size_t smem = 1024 + 2 * KF_ASTAGE + 2 * (size_t)bstage_al + 128 + TAIL_FLOATS * 4 +
+                      (4 * KF_ROWS + KF_ROWS) * sizeof(float2) + (size_t)C * KF_CP * sizeof(float) + 16;
+  if (smem > 227 * 1024) return false;
+  // (i, j) of every 16th feature of the column-major strict upper triangle
+  if (c.koop_start16.n == 0) {
+    std::vector<short2> st;
+    int f = 0;
+    for (int j = 1; j < A; ++j)
+      for (int i = 0; i < j; ++i, ++f)
+        if ((f & 15) == 0) st.push_back(make_short2((short)i, (short)j));
+    st.push_back(make_short2(0, (short)A));
+    c.koop_start16.ensure(st.size());
+    IK_CUDA(cudaMemcpy(c.koop_start16.p, st.data(), st.size() * sizeof(short2), cudaMemcpyHostToDevice));
+  }
+  if (c.attr_needed(Ctx::ATTR_KOOPF))
+    IK_CUDA(cudaFuncSetAttribute(koop_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  alignas(64) CUtensorMap mbh, mbl;
+  make_map(&mbh, g.b_hi, g.N, g.K, g.ldb, nmma_n);
+  make_map(&mbl, g.b_lo, g.N, g.K, g.ldb, nmma_n);
+  KoopFusedP p{};
+  p.coords = coords; p.cmap = c.tri_cmap.p; p.M = M;
+  p.D = c.D; p.A = A; p.F = F; p.C = C;
+  p.nkb = cdiv(F, BK); p.nmma_n = nmma_n;
+  p.do_ln = do_ln ? 1 : 0;
+  p.eps2 = c.cfg.ln_eps * c.cfg.ln_eps;
+  p.start16 = c.koop_start16.p;
+  p.ep.M = (int)M; p.ep.N = g.N; p.ep.K = g.K;
+  p.ep.epi = TC_EPI_TAIL; p.ep.act = g.act; p.ep.bias = g.bias;
+  p.ep.tail = g.tail; p.ep.chi_out = g.chi_out;
+  const int64_t ntiles = (M + KF_ROWS - 1) / KF_ROWS;
+  const int grid = (int)std::min<int64_t>(ntiles, c.num_sms);
+  c.timer.begin(KC_GEMM, c.stream);
+  koop_fused_kernel<<<grid, KF_THREADS, smem, c.stream>>>(mbh, mbl, p);
+  c.timer.end(c.stream);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_GEMM, 2.0 * (double)M * (double)g.N * (double)g.K);
+  c.stats.n_featurize_launches++;
+  if (c.timer.enabled) {
+    c.stats.gemm_mma_flops += 6.0 * (double)M * (double)g.N * (double)g.K;
+    c.stats.featurize_bytes += 4.0 * (double)c.D * (double)M;
+  }
+  return true;
 }
 
 }  // namespace ik
