@@ -191,6 +191,114 @@ struct TcParams {
   int64_t ldz;
 };
 
+// TC_EPI_TAIL: the whole rest of a narrow net per accumulator row -- bias + activation of the tensor-core layer
+// (N <= 128 columns), then the tiny Dense layers (widths <= 16) with their [W; b] rows broadcast from shared memory.
+// One warp = 32 rows of the accumulator.  Written for instruction count: the first ncu capture of the generic
+// version showed ~3000 issued instructions per row (fully unrolled 16 x 16 predicated loops, 64 sigmoids for 38
+// columns) and made the epilogue, not the MMAs or the operand stream, the bound of the kernel (27 % tensor-pipe
+// activity).  Here every loop stops at the real extent with a warp-uniform branch, the first tail layer's padded
+// width CP is a compile-time constant and the first layer's bias comes from shared memory (tailw + kTailBias).
+constexpr int kTailBias = TAIL_FLOATS - 128;   // 128 staged bias values of the tensor-core layer
+
+template <int CP>
+__device__ __forceinline__ void tail_rows(const TcParams &p, uint32_t taddr0, int64_t row, bool row_ok,
+                                          const float *tailw) {
+  float tl[CP];
+#pragma unroll
+  for (int k = 0; k < CP; ++k) tl[k] = 0.f;
+  const float *bias_s = tailw + kTailBias;
+  const bool sig = p.act == ISOKANN_ACT_SIGMOID;
+#pragma unroll 1
+  for (int c = 0; c < p.N; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr0 + c, r);
+    const int nv = p.N - c < 32 ? p.N - c : 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j >= nv) break;  // warp-uniform
+      float v = __uint_as_float(r[j]) + bias_s[c + j];
+      v = sig ? __fdividef(1.0f, 1.0f + __expf(-v)) : act_fwd(v, p.act);
+      const float4 *wr = reinterpret_cast<const float4 *>(tailw + (c + j) * CP);
+#pragma unroll
+      for (int q = 0; q < CP / 4; ++q) {
+        const float4 w4 = wr[q];
+        tl[4 * q] = fmaf(v, w4.x, tl[4 * q]);
+        tl[4 * q + 1] = fmaf(v, w4.y, tl[4 * q + 1]);
+        tl[4 * q + 2] = fmaf(v, w4.z, tl[4 * q + 2]);
+        tl[4 * q + 3] = fmaf(v, w4.w, tl[4 * q + 3]);
+      }
+    }
+  }
+  if (!row_ok) return;
+  float h[16];
+  int off;
+  {
+    const int cols = p.tail.w[1];
+    const float *brow = tailw + p.tail.w[0] * CP;
+    const int kind = p.tail.nl == 1 ? p.tail.last_act : p.tail.act;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) h[k] = (k < CP && k < cols) ? act_fwd(tl[k < CP ? k : 0] + brow[k < CP ? k : 0], kind) : 0.f;
+    off = (p.tail.w[0] + 1) * CP;
+  }
+#pragma unroll 1
+  for (int i = 1; i < p.tail.nl; ++i) {
+    const int rows = p.tail.w[i], cols = p.tail.w[i + 1], cp = (cols + 3) & ~3;
+    float a2[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * q < cp) b4 = *reinterpret_cast<const float4 *>(tailw + off + rows * cp + 4 * q);
+      a2[4 * q] = b4.x; a2[4 * q + 1] = b4.y; a2[4 * q + 2] = b4.z; a2[4 * q + 3] = b4.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j >= rows) break;  // warp-uniform
+      const float4 *wr = reinterpret_cast<const float4 *>(tailw + off + j * cp);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (4 * q >= cp) break;
+        const float4 w4 = wr[q];
+        a2[4 * q] = fmaf(h[j], w4.x, a2[4 * q]);
+        a2[4 * q + 1] = fmaf(h[j], w4.y, a2[4 * q + 1]);
+        a2[4 * q + 2] = fmaf(h[j], w4.z, a2[4 * q + 2]);
+        a2[4 * q + 3] = fmaf(h[j], w4.w, a2[4 * q + 3]);
+      }
+    }
+    const int kind = i == p.tail.nl - 1 ? p.tail.last_act : p.tail.act;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) h[k] = k < cols ? act_fwd(a2[k], kind) : 0.f;
+    off += (rows + 1) * cp;
+  }
+  const int dd = p.tail.w[p.tail.nl];
+#pragma unroll
+  for (int k = 0; k < kMaxD; ++k)
+    if (k < dd) p.chi_out[row * dd + k] = h[k];
+}
+
+__device__ __forceinline__ void tail_rows_any(const TcParams &p, uint32_t taddr0, int64_t row, bool row_ok,
+                                              const float *tailw) {
+  switch ((p.tail.w[1] + 3) >> 2) {
+    case 1: tail_rows<4>(p, taddr0, row, row_ok, tailw); break;
+    case 2: tail_rows<8>(p, taddr0, row, row_ok, tailw); break;
+    case 3: tail_rows<12>(p, taddr0, row, row_ok, tailw); break;
+    default: tail_rows<16>(p, taddr0, row, row_ok, tailw); break;
+  }
+}
+
+// stage the tail layers' [W; b] (rows padded to a multiple of 4 floats) and the tensor-core layer's bias
+__device__ __forceinline__ void stage_tail(const TcParams &p, float *tailw) {
+  int off = 0;
+  for (int i = 0; i < p.tail.nl; ++i) {
+    const int rows = p.tail.w[i] + 1, cols = p.tail.w[i + 1], cp = (cols + 3) & ~3;
+    for (int e = threadIdx.x; e < rows * cp; e += blockDim.x) {
+      const int r = e / cp, cc = e - r * cp;
+      tailw[off + e] = cc < cols ? __ldg(p.tail.seg[i] + (int64_t)r * cols + cc) : 0.f;
+    }
+    off += rows * cp;
+  }
+  for (int e = threadIdx.x; e < 128; e += blockDim.x) tailw[kTailBias + e] = (e < p.N && p.bias) ? __ldg(p.bias + e) : 0.f;
+}
+
 // Epilogue of one 128 x 256 accumulator for one warp (its 32 rows, one 128-column half): shared by the 1-CTA and
 // the 2-CTA kernels.  row0 is the first output row of this CTA's accumulator.
 template <int EPI>
@@ -199,6 +307,10 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, uint32_t tmem_a
   const int64_t row = row0 + quarter * 32 + lane;
   const bool row_ok = row < p.M;
   const uint32_t taddr0 = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+  if (EPI == TC_EPI_TAIL) {  // N <= 128: the whole row belongs to the warps of half 0
+    if (half == 0) tail_rows_any(p, taddr0, row, row_ok, tailw);
+    return;
+  }
   float dot[kMaxD];
 #pragma unroll
   for (int a = 0; a < kMaxD; ++a) dot[a] = 0.f;
@@ -430,15 +542,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   // TC_EPI_TAIL: stage the tail layers' [W; b] in shared memory, rows padded to a multiple of 4 floats
   float *tailw = reinterpret_cast<float *>(base_ptr + STAGES * STAGE_BYTES + 256);
   if (EPI == TC_EPI_TAIL) {
-    int off = 0;
-    for (int i = 0; i < p.tail.nl; ++i) {
-      const int rows = p.tail.w[i] + 1, cols = p.tail.w[i + 1], cp = (cols + 3) & ~3;
-      for (int e = threadIdx.x; e < rows * cp; e += blockDim.x) {
-        const int r = e / cp, cc = e - r * cp;
-        tailw[off + e] = cc < cols ? __ldg(p.tail.seg[i] + (int64_t)r * cols + cc) : 0.f;
-      }
-      off += rows * cp;
-    }
+    stage_tail(p, tailw);
     __syncthreads();
   }
 
@@ -830,17 +934,7 @@ koop_fused_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  {  // tail layers' [W; b], rows padded to a multiple of 4 floats (same layout as tc_gemm_kernel<TC_EPI_TAIL>)
-    int off = 0;
-    for (int i = 0; i < p.ep.tail.nl; ++i) {
-      const int rows = p.ep.tail.w[i] + 1, cols = p.ep.tail.w[i + 1], cp = (cols + 3) & ~3;
-      for (int e = threadIdx.x; e < rows * cp; e += blockDim.x) {
-        const int r = e / cp, cc = e - r * cp;
-        tailw[off + e] = cc < cols ? __ldg(p.ep.tail.seg[i] + (int64_t)r * cols + cc) : 0.f;
-      }
-      off += rows * cp;
-    }
-  }
+  stage_tail(p.ep, tailw);  // tail layers' [W; b] and the first layer's bias
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1126,7 +1220,7 @@ int launch_tc_gemm(Ctx &c, const TcGemm &g) {
       IK_REQUIRE(g.tail.w[i + 1] >= 1 && g.tail.w[i + 1] <= 16, ISOKANN_BAD_ARGUMENT, "tail widths must be <= 16");
       fl += (g.tail.w[i] + 1) * ((g.tail.w[i + 1] + 3) & ~3);
     }
-    IK_REQUIRE(fl <= TAIL_FLOATS && g.tail.w[g.tail.nl] <= kMaxD, ISOKANN_BAD_ARGUMENT, "tail too large");
+    IK_REQUIRE(fl <= TAIL_FLOATS - 128 && g.tail.w[g.tail.nl] <= kMaxD, ISOKANN_BAD_ARGUMENT, "tail too large");
   }
   // 2-CTA pairs for the large K-major GEMMs (forward / data gradient): B crosses L2 -> SMEM once per pair
   const int m_tiles2 = cdiv(g.M, 2 * BM);
