@@ -891,6 +891,44 @@ struct KoopFusedP {
   TcParams ep;               // epilogue parameters (TC_EPI_TAIL)
 };
 
+// 16 consecutive features of the column-major strict upper triangle for one record (lane = record), starting at
+// (i, j).  at: the record's staged coordinates ([coordinate][record], pitch KF_CP).  EMIT == false: accumulate the
+// pivoted LayerNorm sums; EMIT == true: v[k] = d * scale + shift.  i and j are warp-uniform, so the column switch is
+// a non-divergent branch; FULL: all 16 features exist (every k-block but possibly the last).
+template <bool EMIT, bool FULL>
+__device__ __forceinline__ void walk16(const float *at, int i, int j, int nv, float piv, float scale, float shift,
+                                       float &s1, float &s2, float (&v)[16]) {
+  const float *ap = at + 3 * i * KF_CP;   // atom i (row of the pair)
+  const float *cq = at + 3 * j * KF_CP;   // atom j (column of the pair), kept in registers
+  float cx = cq[0], cy = cq[KF_CP], cz = cq[2 * KF_CP];
+  int left = j - i;                       // features left in column j
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if (!FULL && k >= nv) {
+      if (EMIT) v[k] = 0.f;
+      continue;
+    }
+    const float dx = ap[0] - cx, dy = ap[KF_CP] - cy, dz = ap[2 * KF_CP] - cz;
+    const float sq = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+    float d;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(sq));
+    ap += 3 * KF_CP;
+    if (--left == 0) {  // next column (one past the last atom reads the padding rows behind the coordinates)
+      cq += 3 * KF_CP;
+      cx = cq[0]; cy = cq[KF_CP]; cz = cq[2 * KF_CP];
+      ap = at;
+      left = ++j;
+    }
+    if (EMIT) {
+      v[k] = fmaf(d, scale, shift);
+    } else {
+      const float e = d - piv;
+      s1 += e;
+      s2 = fmaf(e, e, s2);
+    }
+  }
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -965,8 +1003,6 @@ koop_fused_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_const
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_all;" ::: "memory");
       named_bar_sync(1, KF_PW * 32);
-      // ---- the walk over this thread's features: 16 consecutive features of every k-block
-      // EMIT == false: LayerNorm sums only; true: normalise, split, store into the A stage
       float scale = 1.f, shift = 0.f;
       // pivot of the variance sums: the record's first distance
       float piv;
@@ -974,81 +1010,59 @@ koop_fused_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_const
         const float dx = at[0] - at[3 * KF_CP], dy = at[KF_CP] - at[4 * KF_CP], dz = at[2 * KF_CP] - at[5 * KF_CP];
         piv = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
       }
-      for (int pass = p.do_ln ? 0 : 1; pass < 2; ++pass) {
-        float s1 = 0.f, s2 = 0.f;
+      // ---- pass 1: LayerNorm statistics (pivoted sums over this thread's quarter of every k-block)
+      if (p.do_ln) {
+        float s1 = 0.f, s2 = 0.f, dummy[16];
         for (int kb = 0; kb < p.nkb; ++kb) {
           const int f0 = kb * 64 + qtr * 16;
-          uint32_t stage = 0, a_hi_s = 0;
-          if (pass == 1) {
-            stage = it & 1u;
-            mbar_wait(bar_aempty + 8 * stage, ((it >> 1) & 1u) ^ 1u);   // the MMAs that read this stage have retired
-            a_hi_s = base + a_off + stage * KF_ASTAGE;
-          }
-          float v[16];
-          if (f0 < p.F) {
-            const short2 st = __ldg(p.start16 + (f0 >> 4));
-            int i = st.x, j = st.y;
-            float cx = at[(3 * j) * KF_CP], cy = at[(3 * j + 1) * KF_CP], cz = at[(3 * j + 2) * KF_CP];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              float d = 0.f;
-              if (f0 + k < p.F) {
-                const float dx = at[(3 * i) * KF_CP] - cx, dy = at[(3 * i + 1) * KF_CP] - cy,
-                            dz = at[(3 * i + 2) * KF_CP] - cz;
-                const float sq = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(sq));
-                if (++i == j) {
-                  i = 0;
-                  ++j;
-                  if (j < p.A) {
-                    cx = at[(3 * j) * KF_CP];
-                    cy = at[(3 * j + 1) * KF_CP];
-                    cz = at[(3 * j + 2) * KF_CP];
-                  }
-                }
-                if (pass == 0) {
-                  const float e = d - piv;
-                  s1 += e;
-                  s2 = fmaf(e, e, s2);
-                }
-              }
-              v[k] = (pass == 1 && f0 + k < p.F) ? fmaf(d, scale, shift) : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = 0.f;
-          }
-          if (pass == 1) {
-            // row `rec` of the K-major, 128B-swizzled tile: 16-byte chunk c of the row sits at chunk c ^ (rec & 7)
-            uint32_t h[8], l[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) split_pair(v[2 * k], v[2 * k + 1], h[k], l[k]);
-            const uint32_t row = a_hi_s + (uint32_t)rec * 128u;
-            const uint32_t c0 = (uint32_t)((2 * qtr) ^ (rec & 7)) << 4, c1 = (uint32_t)((2 * qtr + 1) ^ (rec & 7)) << 4;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c0), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c1), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + KF_ROWS * 128 + c0), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + KF_ROWS * 128 + c1), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_afull + 8 * stage);
-            ++it;
-          }
+          if (f0 >= p.F) break;
+          const short2 st = __ldg(p.start16 + (f0 >> 4));
+          if (f0 + 16 <= p.F) walk16<false, true>(at, st.x, st.y, 16, piv, 1.f, 0.f, s1, s2, dummy);
+          else walk16<false, false>(at, st.x, st.y, p.F - f0, piv, 1.f, 0.f, s1, s2, dummy);
         }
-        if (pass == 0) {
-          part[qtr * KF_ROWS + rec] = make_float2(s1, s2);
-          named_bar_sync(1, KF_PW * 32);
-          float a = 0.f, b = 0.f;
+        part[qtr * KF_ROWS + rec] = make_float2(s1, s2);
+        named_bar_sync(1, KF_PW * 32);
+        float a = 0.f, b = 0.f;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 x = part[q * KF_ROWS + rec];
-            a += x.x;
-            b += x.y;
-          }
-          const float me = a * invF;                                  // mean of (d - pivot)
-          scale = rsqrtf(fmaxf(fmaf(-me, me, b * invF), 0.f) + p.eps2);
-          shift = -(piv + me) * scale;
+        for (int q = 0; q < 4; ++q) {
+          const float2 x = part[q * KF_ROWS + rec];
+          a += x.x;
+          b += x.y;
         }
+        const float me = a * invF;                                  // mean of (d - pivot)
+        scale = rsqrtf(fmaxf(fmaf(-me, me, b * invF), 0.f) + p.eps2);
+        shift = -(piv + me) * scale;
+      }
+      // ---- pass 2: k-block by k-block into the A stages
+      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+        const int f0 = kb * 64 + qtr * 16;
+        const uint32_t stage = it & 1u;
+        mbar_wait(bar_aempty + 8 * stage, ((it >> 1) & 1u) ^ 1u);   // the MMAs that read this stage have retired
+        const uint32_t a_hi_s = base + a_off + stage * KF_ASTAGE;
+        float v[16], u1 = 0.f, u2 = 0.f;
+        if (f0 + 16 <= p.F) {
+          const short2 st = __ldg(p.start16 + (f0 >> 4));
+          walk16<true, true>(at, st.x, st.y, 16, piv, scale, shift, u1, u2, v);
+        } else if (f0 < p.F) {
+          const short2 st = __ldg(p.start16 + (f0 >> 4));
+          walk16<true, false>(at, st.x, st.y, p.F - f0, piv, scale, shift, u1, u2, v);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = 0.f;
+        }
+        // row `rec` of the K-major, 128B-swizzled tile: 16-byte chunk c of the row sits at chunk c ^ (rec & 7)
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) split_pair(v[2 * k], v[2 * k + 1], h[k], l[k]);
+        const uint32_t row = a_hi_s + (uint32_t)rec * 128u;
+        const uint32_t c0 = (uint32_t)((2 * qtr) ^ (rec & 7)) << 4, c1 = (uint32_t)((2 * qtr + 1) ^ (rec & 7)) << 4;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c0), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c1), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + KF_ROWS * 128 + c0), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + KF_ROWS * 128 + c1), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_afull + 8 * stage);
       }
     }
   } else if (warp == KF_PW) {
@@ -1291,7 +1305,7 @@ bool launch_koop_fused(Ctx &c, const float *coords, int64_t M, bool do_ln, const
   const int nmma_n = (g.N + 15) & ~15;
   const int bstage_al = (2 * nmma_n * 128 + 1023) & ~1023;
   const size_t smem = 1024 + 2 * KF_ASTAGE + 2 * (size_t)bstage_al + 128 + TAIL_FLOATS * 4 +
-                      (4 * KF_ROWS + KF_ROWS) * sizeof(float2) + (size_t)C * KF_CP * sizeof(float) + 16;
+                      (4 * KF_ROWS + KF_ROWS) * sizeof(float2) + (size_t)(C + 3) * KF_CP * sizeof(float) + 16;
   if (smem > 227 * 1024) return false;
   // (i, j) of every 16th feature of the column-major strict upper triangle
   if (c.koop_start16.n == 0) {
