@@ -892,33 +892,43 @@ struct KoopFusedP {
 };
 
 // 16 consecutive features of the column-major strict upper triangle for one record (lane = record), starting at
-// (i, j).  at: the record's staged coordinates ([coordinate][record], pitch KF_CP).  EMIT == false: accumulate the
-// pivoted LayerNorm sums; EMIT == true: v[k] = d * scale + shift.  i and j are warp-uniform, so the column switch is
-// a non-divergent branch; FULL: all 16 features exist (every k-block but possibly the last).
+// (i, j).  at: shared-memory address of the record's staged coordinates ([coordinate][record], pitch KF_CP).
+// EMIT == false: accumulate the pivoted LayerNorm sums; EMIT == true: v[k] = d * scale + shift.  i and j are
+// warp-uniform, so the column switch is a non-divergent branch; FULL: all 16 features exist.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// (32-bit shared-window addresses: with generic pointers a third of the issued instructions were 64-bit pointer
+//  arithmetic and generic->shared conversions.)
 template <bool EMIT, bool FULL>
-__device__ __forceinline__ void walk16(const float *at, int i, int j, int nv, float piv, float scale, float shift,
+__device__ __forceinline__ void walk16(uint32_t at, int i, int j, int nv, float piv, float scale, float shift,
                                        float &s1, float &s2, float (&v)[16]) {
-  const float *ap = at + 3 * i * KF_CP;   // atom i (row of the pair)
-  const float *cq = at + 3 * j * KF_CP;   // atom j (column of the pair), kept in registers
-  float cx = cq[0], cy = cq[KF_CP], cz = cq[2 * KF_CP];
-  int left = j - i;                       // features left in column j
+  constexpr uint32_t ROW = 4u * KF_CP;          // bytes between consecutive coordinates of a record
+  uint32_t ap = at + 3u * ROW * (uint32_t)i;    // atom i (row of the pair)
+  uint32_t cq = at + 3u * ROW * (uint32_t)j;    // atom j (column of the pair), kept in registers
+  float cx = lds_f32(cq), cy = lds_f32(cq + ROW), cz = lds_f32(cq + 2 * ROW);
+  int sw = j - i;                               // index k at which the walk moves on to the next column
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     if (!FULL && k >= nv) {
       if (EMIT) v[k] = 0.f;
       continue;
     }
-    const float dx = ap[0] - cx, dy = ap[KF_CP] - cy, dz = ap[2 * KF_CP] - cz;
+    if (k == sw) {  // next column (warp-uniform).  The __syncwarp keeps this a real branch: if-converted, the eight
+      __syncwarp();  // instructions of the switch were issued, predicated off, for every single feature
+      cq += 3 * ROW;
+      cx = lds_f32(cq); cy = lds_f32(cq + ROW); cz = lds_f32(cq + 2 * ROW);
+      ap = at;
+      sw = k + (++j);
+    }
+    const float dx = lds_f32(ap) - cx, dy = lds_f32(ap + ROW) - cy, dz = lds_f32(ap + 2 * ROW) - cz;
     const float sq = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
     float d;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(sq));
-    ap += 3 * KF_CP;
-    if (--left == 0) {  // next column (one past the last atom reads the padding rows behind the coordinates)
-      cq += 3 * KF_CP;
-      cx = cq[0]; cy = cq[KF_CP]; cz = cq[2 * KF_CP];
-      ap = at;
-      left = ++j;
-    }
+    ap += 3 * ROW;
     if (EMIT) {
       v[k] = fmaf(d, scale, shift);
     } else {
@@ -982,7 +992,8 @@ koop_fused_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_const
     // ===================== producers =====================
     const int grp = warp & 3, qtr = warp >> 2;        // record group (32 records), 16-feature quarter of a k-block
     const int rec = grp * 32 + lane;                  // row of the tile
-    const float *at = coord + rec;
+    const float *atp = coord + rec;
+    const uint32_t at = smem_u32(atp);
     const float invF = 1.0f / (float)p.F;
     const uint32_t coord_s = smem_u32(coord);
     uint32_t it = 0;                                  // k-blocks produced so far (stage = it & 1)
@@ -1007,7 +1018,7 @@ koop_fused_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_const
       // pivot of the variance sums: the record's first distance
       float piv;
       {
-        const float dx = at[0] - at[3 * KF_CP], dy = at[KF_CP] - at[4 * KF_CP], dz = at[2 * KF_CP] - at[5 * KF_CP];
+        const float dx = atp[0] - atp[3 * KF_CP], dy = atp[KF_CP] - atp[4 * KF_CP], dz = atp[2 * KF_CP] - atp[5 * KF_CP];
         piv = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
       }
       // ---- pass 1: LayerNorm statistics (pivoted sums over this thread's quarter of every k-block)
