@@ -305,14 +305,19 @@ void forward_rows_tc(Ctx &c, const float *in, const int64_t *gather, int64_t gof
                       c.cfg.last_activation, c.act[c.L].p);
 }
 
+// can forward_rows_tcn run these rows through the fused coordinates -> chi kernel (no x_hat buffers needed)?
+bool koop_fused_applicable(const Ctx &c) {
+  return c.tcn && !c.koop_fused_off && c.tri_n >= 2 && c.tri_n <= 64 && c.cfg.featurizer != ISOKANN_FEAT_IDENTITY &&
+         c.cfg.widths[0] >= 64 && c.cfg.widths[0] == c.tri_n * (c.tri_n - 1) / 2;
+}
+
 void forward_rows_tcn(Ctx &c, const float *in, const int64_t *gather, int64_t goff, int64_t M, bool in_is_coords) {
   TcState &t = *c.tcs;
-  tc_ensure_rows(c, M);
   ensure_tc_weights(c);
   const bool pairs = in_is_coords && c.cfg.featurizer != ISOKANN_FEAT_IDENTITY;
   const int fin = c.cfg.widths[0], fout = c.cfg.widths[1];
+  c.act[c.L].ensure((size_t)M * c.d);
   TcGemm g{};
-  g.a_hi = t.act[0].hi.p; g.a_lo = t.act[0].lo.p; g.lda = t.wp[0];
   g.b_hi = t.wF[0].hi.p; g.b_lo = t.wF[0].lo.p; g.ldb = t.wp[0];
   g.M = (int)M; g.N = fout; g.K = fin;
   g.act = c.cfg.activation;
@@ -325,8 +330,12 @@ void forward_rows_tcn(Ctx &c, const float *in, const int64_t *gather, int64_t go
   for (int l = 1; l < c.L; ++l) g.tail.seg[l - 1] = c.params.p + c.off_w[l];
   g.chi_out = c.act[c.L].p;
   g.splits = 1;
-  // coordinates straight into the tensor-core kernel: x_hat never reaches HBM
-  if (pairs && gather == nullptr && launch_koop_fused(c, in, M, c.ln, g)) return;
+  // coordinates straight into the tensor-core kernel: x_hat never reaches HBM (and needs no buffer, so the caller
+  // may pass millions of rows at once)
+  if (pairs && gather == nullptr && koop_fused_applicable(c) && launch_koop_fused(c, in, M, c.ln, g)) return;
+  tc_ensure_rows(c, M);
+  g.a_hi = t.act[0].hi.p; g.a_lo = t.act[0].lo.p; g.lda = t.wp[0];
+  g.chi_out = c.act[c.L].p;
   launch_featurize_split(c, in, gather, goff, M, pairs, c.ln, t.act[0].hi.p, t.act[0].lo.p, t.wp[0]);
   launch_tc_gemm(c, g);
 }
@@ -519,7 +528,10 @@ void compute_koopman(Ctx &c) {
     c.kchi_loc.ensure((size_t)std::max<int64_t>(1, c.n_loc) * c.d);
     dst = c.kchi_loc.p;
   }
-  const int64_t ch = chunk_rows(c, c.K);
+  // the fused narrow-net kernel has no intermediate buffers: it takes up to 4M rows per launch (no wave
+  // quantisation between 65 536-row chunks, one K-mean launch), unless ys is still streaming in chunk by chunk
+  const bool big = koop_fused_applicable(c) && c.ys_chunk_pts == 0;
+  const int64_t ch = big ? std::max<int64_t>(c.K, ((int64_t)1 << 22) / c.K * c.K) : chunk_rows(c, c.K);
   const int64_t nsp = ch / c.K;
   const bool overlap = c.tc && !c.tcn && c.n_loc > nsp && !c.tc_no_overlap;
   if (overlap) {
