@@ -1332,23 +1332,43 @@ void validate_perm(const int64_t *perm_host, int64_t N) {
 void preload_perm(Ctx &c, const int64_t *perm_host) {
   validate_perm(perm_host, c.N);
   if (!c.copy_stream) IK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-  if (!c.perm_event) IK_CUDA(cudaEventCreateWithFlags(&c.perm_event, cudaEventDisableTiming));
+  if (!c.perm_event) {
+    IK_CUDA(cudaEventCreateWithFlags(&c.perm_event, cudaEventDisableTiming));
+    IK_CUDA(cudaEventCreateWithFlags(&c.perm0_event, cudaEventDisableTiming));
+  }
   c.perm_raw.ensure((size_t)c.N);
   c.perm_dev.ensure((size_t)c.N);
-  IK_CUDA(cudaMemcpyAsync(c.perm_raw.p, perm_host, (size_t)c.N * sizeof(int64_t), cudaMemcpyHostToDevice,
-                          c.copy_stream));
+  // through a page-locked staging buffer: a copy from pageable memory would first drain the copy stream (which may
+  // hold gigabytes of isokann_set_data_async uploads) and block this thread until then
+  const size_t bytes = (size_t)c.N * sizeof(int64_t);
+  if (bytes > c.perm_pinned_bytes) {
+    if (c.perm_pinned) cudaFreeHost(c.perm_pinned);
+    c.perm_pinned = nullptr;
+    c.perm_pinned_bytes = 0;
+    IK_CUDA(cudaMallocHost(&c.perm_pinned, bytes));
+    c.perm_pinned_bytes = bytes;
+  } else if (c.perm_staged) {
+    IK_CUDA(cudaEventSynchronize(c.perm_event));  // the previous permutation has left the staging buffer
+  }
+  memcpy(c.perm_pinned, perm_host, bytes);
+  if (c.perm0_recorded) IK_CUDA(cudaStreamWaitEvent(c.copy_stream, c.perm0_event, 0));  // perm_raw is free again
+  IK_CUDA(cudaMemcpyAsync(c.perm_raw.p, c.perm_pinned, bytes, cudaMemcpyHostToDevice, c.copy_stream));
   IK_CUDA(cudaEventRecord(c.perm_event, c.copy_stream));
+  c.perm_staged = true;
   c.perm_preloaded = perm_host;
+  c.perm_preloaded_n = c.N;
 }
 
-double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool partial) {
+// next_perm: the permutation of the epoch after this one, if the caller already knows it (isokann_iterate): its
+// upload is started while this epoch's steps are still running
+double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool partial, const int64_t *next_perm = nullptr) {
   IK_REQUIRE(c.xs != nullptr, ISOKANN_ERR_STATE, "no data: call isokann_set_data first");
   IK_REQUIRE(c.has_target, ISOKANN_ERR_STATE, "no target: call isokann_target / isokann_set_target first");
   gather_xs(c);
   IK_REQUIRE(perm_host != nullptr, ISOKANN_BAD_ARGUMENT, "perm must not be NULL");
   IK_REQUIRE(minibatch >= 0, ISOKANN_BAD_ARGUMENT, "minibatch must be >= 0");
   const int64_t N = c.N;
-  const bool preloaded = c.perm_preloaded == perm_host;
+  const bool preloaded = c.perm_preloaded == perm_host && c.perm_preloaded_n == N;
   c.perm_preloaded = nullptr;
   if (!preloaded) validate_perm(perm_host, N);
   const int64_t bs = (minibatch == 0 || N < minibatch) ? N : minibatch;  // src/iso.jl:180
@@ -1361,6 +1381,10 @@ double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool par
   else
     IK_CUDA(cudaMemcpyAsync(c.perm_raw.p, perm_host, (size_t)N * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
   launch_perm_to_zero_based(c, c.perm_raw.p, N, c.perm_dev.p);
+  if (c.perm0_event) {
+    IK_CUDA(cudaEventRecord(c.perm0_event, c.stream));
+    c.perm0_recorded = true;
+  }
   IK_CUDA(cudaMemsetAsync(c.epoch_loss.p, 0, sizeof(double), c.stream));
   {
     // every rank gets rows in every step (bs >= world), so all ranks take the same code path
@@ -1424,6 +1448,7 @@ double train_epoch(Ctx &c, const int64_t *perm_host, int64_t minibatch, bool par
     }
   }
   c.timer.end(c.stream);
+  if (next_perm) preload_perm(c, next_perm);  // host-side staging and the DMA run beside this epoch's steps
   double *lp = read_back(c, c.epoch_loss.p, 1);
   const double ls = *lp;
   const int f = check_flags(c);
@@ -1823,6 +1848,8 @@ int32_t isokann_destroy(isokann_ctx *c) {
   for (auto e : c->ys_events) cudaEventDestroy(e);
   if (c->xs_event) cudaEventDestroy(c->xs_event);
   if (c->perm_event) cudaEventDestroy(c->perm_event);
+  if (c->perm0_event) cudaEventDestroy(c->perm0_event);
+  if (c->perm_pinned) cudaFreeHost(c->perm_pinned);
   release_host_registrations(*c);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -2339,12 +2366,14 @@ int32_t isokann_iterate(isokann_ctx *c, int32_t transform, const isokann_target_
   return guarded(c, [&] {
     IK_REQUIRE(perms != nullptr, ISOKANN_BAD_ARGUMENT, "perms must not be NULL");
     int64_t k = 0;
+    const int64_t total = n_iter * epochs;
     for (int64_t it = 0; it < n_iter; ++it) {
       IK_REQUIRE(c->xs != nullptr, ISOKANN_ERR_STATE, "no data: call isokann_set_data first");
-      preload_perm(*c, perms + k * c->N);
+      if (k == 0 && total > 0) preload_perm(*c, perms);
       compute_target(*c, transform, opts);
       for (int64_t e = 0; e < epochs; ++e, ++k) {
-        const double l = train_epoch(*c, perms + k * c->N, minibatch, false);
+        const double l = train_epoch(*c, perms + k * c->N, minibatch, false,
+                                     k + 1 < total ? perms + (k + 1) * c->N : nullptr);
         if (losses_out) losses_out[k] = l;
       }
     }

@@ -240,6 +240,11 @@ struct Ctx {
   int64_t ys_chunks_pending = 0;
   cudaEvent_t perm_event = nullptr;            // the coming epoch's permutation is on its way (preload_perm)
   const int64_t *perm_preloaded = nullptr;     // caller pointer whose contents perm_raw holds / will hold
+  int64_t perm_preloaded_n = 0;
+  cudaEvent_t perm0_event = nullptr;           // perm_raw has been converted (it may be overwritten)
+  bool perm0_recorded = false, perm_staged = false;
+  void *perm_pinned = nullptr;                 // page-locked staging buffer of the permutation upload
+  size_t perm_pinned_bytes = 0;
   cudaEvent_t xs_event = nullptr;  // xs rides the copy stream behind ys (only the training side reads it)
   // cudaFuncSetAttribute is per device: remembered per context, not per process (one process may hold contexts
   // on several devices)

@@ -17,7 +17,7 @@ namespace ik {
 
 namespace {
 
-constexpr int R = 16;          // minibatch rows per group
+constexpr int RMAX = 16;       // minibatch rows per group: 16, or 8 when 16-row groups would leave SMs idle
 constexpr int H1P = 128;       // padded first hidden width
 constexpr int TW = 16;         // padded tail width
 constexpr int NT = 512;        // 128 columns x 4 k-quarters
@@ -58,6 +58,7 @@ __device__ __forceinline__ float dactf(float z, int kind) {
   }
 }
 
+template <int R>
 __global__ void __launch_bounds__(NT) narrow_fwd_bwd_kernel(NarrowP p) {
   extern __shared__ __align__(16) float sm[];
   float *xT = sm;                                 // [F][R]
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(NT) narrow_fwd_bwd_kernel(NarrowP p) {
     __syncthreads();
     // (1) x_hat rows of this group, transposed: xT[k][r]
     for (int e = tid; e < R * p.F; e += NT) {
-      const int r = e & (R - 1), k = e >> 4;
+      const int r = e & (R - 1), k = e / R;
       const int row = row0 + r;
       xT[e] = row < p.B ? __ldg(p.xhat + (int64_t)row * p.ldx + k) : 0.f;
     }
@@ -117,16 +118,15 @@ __global__ void __launch_bounds__(NT) narrow_fwd_bwd_kernel(NarrowP p) {
 #pragma unroll
           for (int u = 0; u < PF; ++u) {
             const int k = kk[u];
-            const float4 a = x4[k * 4], b = x4[k * 4 + 1], c = x4[k * 4 + 2], e = x4[k * 4 + 3];
             const float w = wv[u];
-            acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]);
-            acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
-            acc[4] = fmaf(b.x, w, acc[4]); acc[5] = fmaf(b.y, w, acc[5]);
-            acc[6] = fmaf(b.z, w, acc[6]); acc[7] = fmaf(b.w, w, acc[7]);
-            acc[8] = fmaf(c.x, w, acc[8]); acc[9] = fmaf(c.y, w, acc[9]);
-            acc[10] = fmaf(c.z, w, acc[10]); acc[11] = fmaf(c.w, w, acc[11]);
-            acc[12] = fmaf(e.x, w, acc[12]); acc[13] = fmaf(e.y, w, acc[13]);
-            acc[14] = fmaf(e.z, w, acc[14]); acc[15] = fmaf(e.w, w, acc[15]);
+#pragma unroll
+            for (int q = 0; q < R / 4; ++q) {
+              const float4 a = x4[k * (R / 4) + q];
+              acc[4 * q] = fmaf(a.x, w, acc[4 * q]);
+              acc[4 * q + 1] = fmaf(a.y, w, acc[4 * q + 1]);
+              acc[4 * q + 2] = fmaf(a.z, w, acc[4 * q + 2]);
+              acc[4 * q + 3] = fmaf(a.w, w, acc[4 * q + 3]);
+            }
           }
         }
         if (kh) {
@@ -245,13 +245,18 @@ __global__ void __launch_bounds__(NT) narrow_fwd_bwd_kernel(NarrowP p) {
         for (int k = k0; k < k1; ++k) {
           float s = 0.f;
           if (k < p.F) {
-            const float4 a = x4[k * 4], b = x4[k * 4 + 1], c = x4[k * 4 + 2], e = x4[k * 4 + 3];
-            // four independent partial sums: a single 16-deep FMA chain exposed its full latency
-            float s0 = a.x * dc[0], s1 = b.x * dc[4], s2 = c.x * dc[8], s3 = e.x * dc[12];
-            s0 = fmaf(a.y, dc[1], s0); s1 = fmaf(b.y, dc[5], s1); s2 = fmaf(c.y, dc[9], s2); s3 = fmaf(e.y, dc[13], s3);
-            s0 = fmaf(a.z, dc[2], s0); s1 = fmaf(b.z, dc[6], s1); s2 = fmaf(c.z, dc[10], s2); s3 = fmaf(e.z, dc[14], s3);
-            s0 = fmaf(a.w, dc[3], s0); s1 = fmaf(b.w, dc[7], s1); s2 = fmaf(c.w, dc[11], s2); s3 = fmaf(e.w, dc[15], s3);
-            s = (s0 + s1) + (s2 + s3);
+            // independent partial sums per float4: a single R-deep FMA chain exposed its full latency
+            float ps[R / 4];
+#pragma unroll
+            for (int q = 0; q < R / 4; ++q) {
+              const float4 a = x4[k * (R / 4) + q];
+              float t = a.x * dc[4 * q];
+              t = fmaf(a.y, dc[4 * q + 1], t);
+              t = fmaf(a.z, dc[4 * q + 2], t);
+              ps[q] = fmaf(a.w, dc[4 * q + 3], t);
+            }
+            if (R == 16) s = (ps[0] + ps[1]) + (ps[2 % (R / 4)] + ps[3 % (R / 4)]);
+            else s = ps[0] + ps[1 % (R / 4)];
           } else {
 #pragma unroll
             for (int r = 0; r < R; ++r) s += dc[r];
@@ -389,7 +394,7 @@ bool narrow_train_eligible(const isokann_config &g) {
     if (g.widths[l] > TW) return false;
   if (g.widths[g.n_layers] > kMaxD) return false;
   // x_hat tile + activations must fit shared memory
-  const size_t smem = ((size_t)g.widths[0] * R + (2 + KQ - 1) * R * H1P + 2 * ISOKANN_MAX_LAYERS * R * TW) * sizeof(float);
+  const size_t smem = ((size_t)g.widths[0] * RMAX + (2 + KQ - 1) * RMAX * H1P + 2 * ISOKANN_MAX_LAYERS * RMAX * TW) * sizeof(float);
   return smem <= 200 * 1024;
 }
 
@@ -411,6 +416,8 @@ void launch_narrow_train(Ctx &c, const float *xhat, int64_t Bloc, const int64_t 
   p.off[L] = off;
   p.target = c.target.p; p.idx = idx; p.wloss = c.w_loss.p; p.Bglobal = Bglobal;
   p.act = c.cfg.activation; p.last_act = c.cfg.last_activation;
+  // 16-row groups unless they would leave a third of the SMs without work (B = 1000: 63 groups on 148 SMs)
+  const int R = cdiv(Bloc, RMAX) * 3 < c.num_sms * 2 ? 8 : RMAX;
   p.groups = cdiv(Bloc, R);
   const int nparts = std::min(p.groups, 2 * c.num_sms);
   const int64_t stride = (off + 3) & ~(int64_t)3;
@@ -418,10 +425,13 @@ void launch_narrow_train(Ctx &c, const float *xhat, int64_t Bloc, const int64_t 
   c.red_d.ensure((size_t)std::max(nparts, 1024));
   p.part = c.splitk.p; p.part_stride = stride; p.part_loss = c.red_d.p;
   const size_t smem = ((size_t)F * R + (2 + KQ - 1) * R * H1P + 2 * ISOKANN_MAX_LAYERS * R * TW) * sizeof(float);
-  if (c.attr_needed(Ctx::ATTR_NARROW))
-    IK_CUDA(cudaFuncSetAttribute(narrow_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if (c.attr_needed(Ctx::ATTR_NARROW)) {
+    IK_CUDA(cudaFuncSetAttribute(narrow_fwd_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    IK_CUDA(cudaFuncSetAttribute(narrow_fwd_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
   c.timer.begin(KC_GEMM, c.stream);
-  narrow_fwd_bwd_kernel<<<nparts, NT, smem, c.stream>>>(p);
+  if (R == 8) narrow_fwd_bwd_kernel<8><<<nparts, NT, smem, c.stream>>>(p);
+  else narrow_fwd_bwd_kernel<16><<<nparts, NT, smem, c.stream>>>(p);
   c.timer.end(c.stream);
   IK_CUDA(cudaGetLastError());
   double macs = 0;
