@@ -112,8 +112,12 @@ __global__ void __launch_bounds__(NT) narrow_fwd_bwd_kernel(NarrowP p) {
           for (int u = 0; u < PF; ++u) {
             int k = kb + u + rot;
             if (k >= len) k -= len;
-            kk[u] = k0 + k;
-            wv[u] = kb + u < len ? __ldg(wcol + (int64_t)kk[u] * h1) : 0.f;
+            // slots past the end of this thread's k range multiply a zero weight, but the x they read must still be
+            // finite: row k0 of the staged tile (rows beyond F are uninitialised shared memory -- a NaN pattern left
+            // there by another kernel turned every gradient of the F = 2 triple-well net into NaN on multi-rank runs)
+            const bool live = kb + u < len;
+            kk[u] = live ? k0 + k : k0;
+            wv[u] = live ? __ldg(wcol + (int64_t)kk[u] * h1) : 0.f;
           }
 #pragma unroll
           for (int u = 0; u < PF; ++u) {
