@@ -1467,16 +1467,18 @@ void upload_rows(Ctx &c, const void *host, bool f64, int64_t count, float *dev) 
     return;
   }
   // Float64 coordinates: the reference featurizes in the input eltype and casts the features to
-  // Float32 (src/simulation.jl:112); here coordinates are rounded to Float32 on upload.
+  // Float32 (src/simulation.jl:112); here coordinates are rounded to Float32 once, on the device (with direct
+  // differences that keeps distances within 2e-6 relative of the Float64 result).  The doubles go up in 32 MiB
+  // pieces through a device staging buffer, so the host does no conversion work and never waits per piece.
   const int64_t blk = 1 << 22;
-  std::vector<float> tmp((size_t)std::min(blk, count));
+  c.staging_f64.ensure((size_t)std::min(blk, count));
   const double *src = (const double *)host;
   for (int64_t o = 0; o < count; o += blk) {
     const int64_t n = std::min(blk, count - o);
-    for (int64_t i = 0; i < n; ++i) tmp[i] = (float)src[o + i];
-    IK_CUDA(cudaMemcpyAsync(dev + o, tmp.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c.stream));
-    sync_stream(c);
+    IK_CUDA(cudaMemcpyAsync(c.staging_f64.p, src + o, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    launch_f64_to_f32(c, c.staging_f64.p, n, dev + o);
   }
+  sync_stream(c);
 }
 
 // Page-lock caller memory for the asynchronous upload (cudaHostRegister) so that the DMA engine reads it directly
@@ -1527,60 +1529,66 @@ void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_pt
   split_range(N, c.world, c.rank, &eo, &el);
   IK_REQUIRE(n_off == eo && n_loc == el, ISOKANN_BAD_ARGUMENT,
              "shard does not follow the contiguous split rule (see isokann_set_data_sharded)");
+  // while the upload is under way the context holds no data: if anything below throws, later calls report
+  // "no data" instead of running on a half-updated shard description
   c.has_target = false;
   c.has_weights = false;
-  c.N = N; c.K = K; c.n_off = n_off; c.n_loc = n_loc;
+  c.xs = nullptr;
+  c.ys = nullptr;
   if (dev_ptrs) {
+    c.N = N; c.K = K; c.n_off = n_off; c.n_loc = n_loc;
     c.xs = (const float *)xs;
     c.ys = (const float *)ys;
-  } else {
-    c.xs_own.ensure((size_t)N * D);
-    const bool async_all = async_ys && !f64 && ys && K > 0 && n_loc > 0;
-    if (!async_all) upload_rows(c, xs, f64, N * D, c.xs_own.p);
-    c.xs = c.xs_own.p;
-    c.ys = nullptr;
-    if (ys && K > 0 && n_loc > 0) {
-      c.ys_own.ensure((size_t)n_loc * K * D);
-      if (async_ys && !f64) {
-        // stream ys in on a second stream, ~64 MiB per chunk, one event per chunk; the Koopman pass waits per
-        // chunk, so the PCIe transfer overlaps the forward pass over the chunks that already arrived
-        if (!c.copy_stream) IK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-        ensure_host_registered(c, 0, ys, (size_t)n_loc * K * D * sizeof(float));
-        ensure_host_registered(c, 1, xs, (size_t)N * D * sizeof(float));
-        const int64_t pts = std::max<int64_t>(1, (64ll << 20) / (K * D * 4));
-        const int64_t nchunks = (n_loc + pts - 1) / pts;
-        while ((int64_t)c.ys_events.size() < nchunks) {
-          cudaEvent_t e;
-          IK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-          c.ys_events.push_back(e);
-        }
-        const float *src = (const float *)ys;
-        for (int64_t i = 0; i < nchunks; ++i) {
-          const int64_t p0 = i * pts, np = std::min(pts, n_loc - p0);
-          IK_CUDA(cudaMemcpyAsync(c.ys_own.p + p0 * K * D, src + p0 * K * D, (size_t)np * K * D * sizeof(float),
-                                  cudaMemcpyHostToDevice, c.copy_stream));
-          IK_CUDA(cudaEventRecord(c.ys_events[(size_t)i], c.copy_stream));
-        }
-        c.ys_chunk_pts = pts;
-        c.ys_chunks_pending = nchunks;
-        // xs last: the Koopman pass reads ys only, so xs arrives while that pass is already running
-        if (!c.xs_event) IK_CUDA(cudaEventCreateWithFlags(&c.xs_event, cudaEventDisableTiming));
-        if (c.world > 1) {  // only this rank's rows cross PCIe; gather_xs() fetches the rest from the peers
-          IK_CUDA(cudaMemcpyAsync(c.xs_own.p + n_off * D, (const float *)xs + n_off * D,
-                                  (size_t)n_loc * D * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
-          c.xs_gather_pending = true;
-        } else {
-          IK_CUDA(cudaMemcpyAsync(c.xs_own.p, xs, (size_t)N * D * sizeof(float), cudaMemcpyHostToDevice,
-                                  c.copy_stream));
-        }
-        IK_CUDA(cudaEventRecord(c.xs_event, c.copy_stream));
-        c.xs_pending = true;
-      } else {
-        upload_rows(c, ys, f64, n_loc * K * D, c.ys_own.p);
-      }
-      c.ys = c.ys_own.p;
-    }
+    return;
   }
+  c.xs_own.ensure((size_t)N * D);
+  const bool have_ys = K > 0 && (ys != nullptr || n_loc == 0);
+  // the asynchronous path (and with it the later all-gather of xs) must be taken by every rank or by none: decide on
+  // values that are the same everywhere (K, element type, the entry point), never on this rank's shard size
+  const bool async_all = async_ys && !f64 && K > 0;
+  IK_REQUIRE(!async_all || have_ys, ISOKANN_BAD_ARGUMENT, "isokann_set_data_async needs the Koopman samples of this shard");
+  if (!async_all) upload_rows(c, xs, f64, N * D, c.xs_own.p);
+  if (K > 0 && n_loc > 0 && ys != nullptr) c.ys_own.ensure((size_t)n_loc * K * D);
+  if (async_all) {
+    // stream ys in on a second stream, ~64 MiB per chunk, one event per chunk; the Koopman pass waits per
+    // chunk, so the PCIe transfer overlaps the forward pass over the chunks that already arrived
+    if (!c.copy_stream) IK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    ensure_host_registered(c, 0, n_loc > 0 ? ys : nullptr, (size_t)n_loc * K * D * sizeof(float));
+    ensure_host_registered(c, 1, xs, (size_t)N * D * sizeof(float));
+    const int64_t pts = std::max<int64_t>(1, (64ll << 20) / (K * D * 4));
+    const int64_t nchunks = (n_loc + pts - 1) / pts;
+    while ((int64_t)c.ys_events.size() < nchunks) {
+      cudaEvent_t e;
+      IK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c.ys_events.push_back(e);
+    }
+    const float *src = (const float *)ys;
+    for (int64_t i = 0; i < nchunks; ++i) {
+      const int64_t p0 = i * pts, np = std::min(pts, n_loc - p0);
+      IK_CUDA(cudaMemcpyAsync(c.ys_own.p + p0 * K * D, src + p0 * K * D, (size_t)np * K * D * sizeof(float),
+                              cudaMemcpyHostToDevice, c.copy_stream));
+      IK_CUDA(cudaEventRecord(c.ys_events[(size_t)i], c.copy_stream));
+    }
+    // xs last: the Koopman pass reads ys only, so xs arrives while that pass is already running
+    if (!c.xs_event) IK_CUDA(cudaEventCreateWithFlags(&c.xs_event, cudaEventDisableTiming));
+    if (c.world > 1) {  // only this rank's rows cross PCIe; gather_xs() fetches the rest from the peers
+      if (n_loc > 0)
+        IK_CUDA(cudaMemcpyAsync(c.xs_own.p + n_off * D, (const float *)xs + n_off * D,
+                                (size_t)n_loc * D * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+    } else {
+      IK_CUDA(cudaMemcpyAsync(c.xs_own.p, xs, (size_t)N * D * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+    }
+    IK_CUDA(cudaEventRecord(c.xs_event, c.copy_stream));
+    c.ys_chunk_pts = nchunks > 0 ? pts : 0;
+    c.ys_chunks_pending = nchunks;
+    c.xs_gather_pending = c.world > 1;
+    c.xs_pending = true;
+  } else if (K > 0 && n_loc > 0 && ys != nullptr) {
+    upload_rows(c, ys, f64, n_loc * K * D, c.ys_own.p);
+  }
+  c.N = N; c.K = K; c.n_off = n_off; c.n_loc = n_loc;
+  c.xs = c.xs_own.p;
+  c.ys = (K > 0 && n_loc > 0 && ys != nullptr) ? c.ys_own.p : nullptr;
 }
 
 void build_pair_table(Ctx &c) {
@@ -1798,6 +1806,7 @@ int32_t isokann_destroy(isokann_ctx *c) {
                          &c->kweights, &c->chi_x, &c->kchi, &c->kchi_loc, &c->gather_pad, &c->target, &c->w_loss,
                          &c->delta_a, &c->delta_b, &c->splitk, &c->staging_in, &c->staging_out, &c->red_f,
                          &c->xs_stage, &c->val_chi, &c->val_k1, &c->beta_dev};
+  c->staging_f64.release();
   for (auto *b : fb) b->release();
   if (c->tcs) {
     for (auto &b : c->tcs->act) b.release();

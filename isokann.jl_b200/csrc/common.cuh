@@ -142,6 +142,7 @@ void launch_kmean(Ctx &c, const float *chi, const float *weights, int64_t n, int
 void launch_minmax(Ctx &c, const float *x, int64_t n, float *partials, int *nblocks_out);
 void launch_shiftscale(Ctx &c, const float *x, int64_t n, const float *partials, int nblocks, float *out, int *flags);
 void launch_fill(Ctx &c, float *x, int64_t n, float v);
+void launch_f64_to_f32(Ctx &c, const double *in, int64_t n, float *out);
 void launch_valloss(Ctx &c, const float *chi, const float *k1, int64_t n, float mn, float mx, double *partials,
                     int *nblocks_out);
 void launch_gram(Ctx &c, const float *chi, const float *kchi, int64_t n, int d, double *partials, int *nblocks_out);
@@ -276,7 +277,7 @@ struct Ctx {
   // workspaces
   std::vector<DevBuf<float>> act;  // act[l]: rows x widths[l]
   DevBuf<float> delta_a, delta_b, splitk, staging_in, staging_out, red_f;
-  DevBuf<double> red_d, epoch_loss;
+  DevBuf<double> red_d, epoch_loss, staging_f64;
   DevBuf<ArgmaxPartial> red_am;
   DevBuf<int64_t> perm_dev, perm_raw;
   DevBuf<int> flags;

@@ -37,8 +37,10 @@ __device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, f
 
 // Columns j0 .. j0+JT-1 of the strict upper triangle against all atoms i < j.  at = staged atoms + lane,
 // dt = parked-distance row of feature (0, j0) + lane.  Feature (i, j0+k) sits k*j0 + k(k-1)/2 + i rows after dt.
+// s, q accumulate the LayerNorm sums about the pivot piv (the record's first distance): sum(d - piv) and
+// sum((d - piv)^2).  The plain single-pass form E[d^2] - mu^2 cancels for large offsets / nearly uniform distances.
 template <int JT, int SC>  // SC: words between consecutive coordinates of one record in the staged block
-__device__ __forceinline__ void sweep_tile(const float *at, int j0, float &s, float &q, float *dt) {
+__device__ __forceinline__ void sweep_tile(const float *at, int j0, float piv, float &s, float &q, float *dt) {
   float cx[JT], cy[JT], cz[JT];
 #pragma unroll
   for (int k = 0; k < JT; ++k) {
@@ -64,8 +66,9 @@ __device__ __forceinline__ void sweep_tile(const float *at, int j0, float &s, fl
     for (int k = 0; k < JT; ++k) {
       float sq;
       const float d = dist3(ax, ay, az, cx[k], cy[k], cz[k], sq);
-      s2[k] += d;
-      q2[k] += sq;
+      const float e = d - piv;
+      s2[k] += e;
+      q2[k] = fmaf(e, e, q2[k]);
       dp[(k * j0 + (k * (k - 1)) / 2) * RP] = d;
     }
     ax = bx, ay = by, az = bz;
@@ -79,8 +82,9 @@ __device__ __forceinline__ void sweep_tile(const float *at, int j0, float &s, fl
     for (int k = t + 1; k < JT; ++k) {
       float sq;
       const float d = dist3(cx[t], cy[t], cz[t], cx[k], cy[k], cz[k], sq);
-      s2[k] += d;
-      q2[k] += sq;
+      const float e = d - piv;
+      s2[k] += e;
+      q2[k] = fmaf(e, e, q2[k]);
       dt[(k * j0 + (k * (k - 1)) / 2 + j0 + t) * RP] = d;
     }
   }
@@ -162,6 +166,12 @@ __global__ void __launch_bounds__(256, 2)
     issue(blk);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();  // atoms complete; every warp has left pass 2 of the previous block
+    // pivot of the LayerNorm sums: the record's first distance (atoms 0 and 1); the same in every warp
+    float piv;
+    {
+      float sq;
+      piv = dist3(at[0], at[RP], at[2 * RP], at[3 * RP], at[4 * RP], at[5 * RP], sq);
+    }
     // ---- pass 1: distances -> shared memory, partial LayerNorm sums per warp
     {
       float s = 0.f, q = 0.f;
@@ -173,8 +183,8 @@ __global__ void __launch_bounds__(256, 2)
           if (u < T) {
             const int j0 = 1 + 2 * (T - 1 - u);
             float *dt = dist + ((j0 * (j0 - 1)) >> 1) * RP + lane;
-            if (j0 + 1 < A) sweep_tile<2, RP>(at, j0, s, q, dt);
-            else sweep_tile<1, RP>(at, j0, s, q, dt);
+            if (j0 + 1 < A) sweep_tile<2, RP>(at, j0, piv, s, q, dt);
+            else sweep_tile<1, RP>(at, j0, piv, s, q, dt);
           }
         }
       }
@@ -191,9 +201,9 @@ __global__ void __launch_bounds__(256, 2)
           s += p.x;
           q += p.y;
         }
-        const float mu = s * invF;
-        scale = rsqrtf(fmaxf(fmaf(-mu, mu, q * invF), 0.f) + eps2);
-        shift = -mu * scale;
+        const float me = s * invF;  // mean of (d - pivot)
+        scale = rsqrtf(fmaxf(fmaf(-me, me, q * invF), 0.f) + eps2);
+        shift = -(piv + me) * scale;
       }
       stat[w * 32 + lane] = make_float2(scale, shift);
       __syncwarp();

@@ -363,6 +363,18 @@ void launch_valloss(Ctx &c, const float *chi, const float *k1, int64_t n, float 
   *nblocks_out = grid;
 }
 
+// ---- Float64 coordinates -> Float32 (round to nearest), isokann_set_data_f64 ----
+__global__ void f64_to_f32_kernel(const double *__restrict__ in, int64_t n, float *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (float)in[i];
+}
+void launch_f64_to_f32(Ctx &c, const double *in, int64_t n, float *out) {
+  if (n <= 0) return;
+  f64_to_f32_kernel<<<red_grid(c, n), kRedThreads, 0, c.stream>>>(in, n, out);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_REDUCE);
+}
+
 // ---- perm (1-based, Julia) -> 0-based device indices ----
 __global__ void perm0_kernel(const int64_t *__restrict__ p1, int64_t n, int64_t *__restrict__ p0) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)

@@ -35,6 +35,28 @@ def rank_batch_slice(perm1: np.ndarray, start: int, length: int, world: int, ran
     return np.asarray(perm1[start + off:start + off + n])
 
 
+def exchange_slices(lo: int, hi: int, world: int):
+    """Who sums what in the gradient exchange over peer memory (csrc/p2p.cu): the flat range [lo, hi) is cut on
+    4-element boundaries of the global index; rank r owns the r-th of `world` equal runs of float4 vectors, rank 0
+    additionally the unaligned head and tail.  Returns per rank a list of (start, stop) element ranges."""
+    lo4, hi4 = (lo + 3) & ~3, hi & ~3
+    out = [[] for _ in range(world)]
+    if hi4 > lo4:
+        nvec = (hi4 - lo4) >> 2
+        per = -(-nvec // world)
+        for r in range(world):
+            v0, v1 = min(nvec, per * r), min(nvec, per * r + per)
+            if v1 > v0:
+                out[r].append((lo4 + 4 * v0, lo4 + 4 * v1))
+    head_end = min(lo4, hi)
+    tail_start = max(hi4, head_end)
+    if head_end > lo:
+        out[0].append((lo, head_end))
+    if hi > tail_start:
+        out[0].append((tail_start, hi))
+    return out
+
+
 def broadcast_unique_id(rank: int, src: int = 0) -> Optional[bytes]:
     """rank ``src`` creates the NCCL unique id, torch.distributed broadcasts it to everyone"""
     import torch.distributed as dist

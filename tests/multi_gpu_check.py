@@ -28,13 +28,16 @@ def main():
                                                 ("c4", [231, 38, 6, 2], "isa", 640, 2, 0, "auto"),
                                                 ("c1", [231, 256, 256, 1], "shiftscale", 900, 2, 300, "tc"),
                                                 ("c4", [231, 256, 264, 3], "pinv_default", 1200, 2, 400, "tc"),
-                                                ("c1", [231, 512, 1], "shiftscale", 700, 2, 0, "tc")]:
+                                                ("c1", [231, 512, 1], "shiftscale", 700, 2, 0, "tc"),
+                                                # triple well: identity featurizer, no LayerNorm, F = 2 (the fused
+                                                # narrow step once read uninitialised shared memory here)
+                                                ("c2", None, "shiftscale", 1000, 3, 250, "auto")]:
         w = copy.deepcopy(pkg.synthetic.WORKLOADS[name])
         if widths:
             w.widths = widths
         xs, ys = pkg.synthetic.make_data(w, N, K)
         perms = pkg.synthetic.make_perms(w, N, 3)
-        model = pkg.densenet(w.widths, layernorm=True, rng=np.random.default_rng(7))
+        model = pkg.densenet(w.widths, layernorm=w.layernorm, rng=np.random.default_rng(7))
         flat0 = model.flat()
         tobj = {"shiftscale": pkg.TransformShiftscale, "isa": pkg.TransformISA, "pinv": pkg.TransformPseudoInv,
                 "pinv_default": pkg.TransformPseudoInv}[target]()
@@ -42,8 +45,9 @@ def main():
             tobj = pkg.TransformPseudoInv(eigenvecs=False)   # Schur vectors are rounding-sensitive
 
         def make(comm):
-            m = pkg.Chain(list(w.widths), True).load_flat(flat0)
-            data = pkg.SimulationData(xs, ys, featurizer=pkg.FeaturesAll())
+            m = pkg.Chain(list(w.widths), w.layernorm).load_flat(flat0)
+            feat = pkg.FeaturesAll() if w.featurizer == "allpairs" else pkg.FeaturesCoords()
+            data = pkg.SimulationData(xs, ys, featurizer=feat)
             return pkg.Iso(data, opt=pkg.AdamRegularized(), model=m, target=tobj, minibatch=B, device=local, gemm=gemm,
                            comm=comm)
         uid = pkg.parallel.broadcast_unique_id(rank)      # a communicator needs its own fresh id

@@ -91,3 +91,22 @@ def test_iso_rejects_cpu_and_mismatched_model(pkg):
         pkg.Iso(data, gpu=False)
     with pytest.raises(AssertionError):
         pkg.Iso(data, model=pkg.pairnet(n=7))                    # featuredim is 1
+
+
+def test_exchange_slices_cover_every_element_once(pkg):
+    """the ownership rule of the peer-memory gradient exchange (csrc/p2p.cu mirrors parallel.exchange_slices):
+    every element of [lo, hi) is summed by exactly one rank, vector runs start on 16-byte boundaries"""
+    par = pkg.parallel
+    for world in (2, 3, 4, 8):
+        for lo, hi in ((0, 179), (1221798, 5420201), (0, 1221798), (5, 7), (8, 20), (3, 4), (0, 44093), (7, 7)):
+            owner = {}
+            for r, runs in enumerate(par.exchange_slices(lo, hi, world)):
+                for a, b in runs:
+                    assert lo <= a < b <= hi
+                    for i in range(a, b) if b - a < 4096 else (a, (a + b) // 2, b - 1):
+                        assert i not in owner, (lo, hi, world, i)
+                        owner[i] = r
+                    if b - a >= 4 and (a % 4 == 0):
+                        assert (b - a) % 4 == 0 or r == 0
+            covered = sum(b - a for runs in par.exchange_slices(lo, hi, world) for a, b in runs)
+            assert covered == hi - lo, (lo, hi, world, covered)
