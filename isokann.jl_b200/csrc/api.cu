@@ -1548,7 +1548,9 @@ void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_pt
   const bool async_all = async_ys && !f64 && K > 0;
   IK_REQUIRE(!async_all || have_ys, ISOKANN_BAD_ARGUMENT, "isokann_set_data_async needs the Koopman samples of this shard");
   if (!async_all) upload_rows(c, xs, f64, N * D, c.xs_own.p);
-  if (K > 0 && n_loc > 0 && ys != nullptr) c.ys_own.ensure((size_t)n_loc * K * D);
+  // a rank whose shard is empty (N < world) still owns a (1-element) sample buffer, so that it enters the Koopman
+  // pass and its collectives like everybody else
+  if (have_ys) c.ys_own.ensure((size_t)std::max<int64_t>(1, n_loc * K * D));
   if (async_all) {
     // stream ys in on a second stream, ~64 MiB per chunk, one event per chunk; the Koopman pass waits per
     // chunk, so the PCIe transfer overlaps the forward pass over the chunks that already arrived
@@ -1588,7 +1590,7 @@ void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_pt
   }
   c.N = N; c.K = K; c.n_off = n_off; c.n_loc = n_loc;
   c.xs = c.xs_own.p;
-  c.ys = (K > 0 && n_loc > 0 && ys != nullptr) ? c.ys_own.p : nullptr;
+  c.ys = have_ys ? c.ys_own.p : nullptr;
 }
 
 void build_pair_table(Ctx &c) {
