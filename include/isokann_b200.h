@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ISOKANN_ABI_VERSION 2
+#define ISOKANN_ABI_VERSION 3
 #define ISOKANN_MAX_LAYERS 8
 
 /* status codes; 1..4 are the reference's DomainErrors and must be re-thrown as such */
@@ -207,6 +207,30 @@ int32_t isokann_download_target(isokann_ctx *ctx, float *target_out);
  * One dimensional chi only (it shift-scales); ISOKANN_DOMAIN_CONSTANT_CHI as src/isotarget.jl:39. */
 int32_t isokann_validationloss(isokann_ctx *ctx, const float *vxs, const float *vys, int64_t D, int64_t K, int64_t Nv,
                                double *loss_out);
+/* Diagnostics on the resident data (loggers call them every `logevery` iterations; in the reference each of them pulls
+ * chi and Kchi to the host).  chi = chis(iso), Kchi = koopman(iso) are evaluated on the device, their second moments
+ * and the residual column norms are fp64 device reductions, the d x d algebra runs on the host in double precision
+ * (the reference: Float32 `/` and `log` for rates, Float64 for the residuals).  With several ranks every rank returns
+ * the same result.  Matrices are column-major as in Julia.
+ *
+ * rates(iso) (src/iso.jl:339-351) WITHOUT the division by lagtime(sim): Q = log(Kchi / chi), `/` the least-squares
+ * right division.  One dimensional chi: rows [chi; 1 - chi] and [Kchi; 1 - Kchi] (:346-349), Q is 2 x 2.
+ * q_colmajor: dim x dim doubles, dim = max(d, 2) returned in *dim_out (may be NULL).  ISOKANN_BAD_ARGUMENT if Kchi / chi
+ * has an eigenvalue on the closed negative real axis (the reference's `log` turns complex there). */
+int32_t isokann_rates(isokann_ctx *ctx, double *q_colmajor, int32_t *dim_out);
+/* residual_subspace(iso) (src/isotarget.jl:805-821): V = chis(iso)', KV = koopman(iso)' (N x d, Float64),
+ * res = KV - Q Q' KV with Q of the thin QR of V, relres[j] = |res[:, j]| / |KV[:, j]| (v_norms != 0: / |V[:, j]|).
+ * relres_out: d doubles.  res_out: N x d doubles or NULL (then only d numbers leave the device). */
+int32_t isokann_residual_subspace(isokann_ctx *ctx, int32_t v_norms, double *relres_out, double *res_out);
+/* residual_ritz(iso) (src/isotarget.jl:787-802): Kr = Q' KV R^-1 (V = Q R), eigen(Kr, sortby = x -> abs(1 - x)),
+ * residues = KQ vecs - vals' .* (Q vecs), relres[j] = |residues[:, j]| / |(KQ vecs)[:, j]|.
+ * vals_out: d complex numbers (re, im interleaved); vecs_out: d x d complex, column-major, interleaved, or NULL --
+ * eigenvectors of Kr in the basis Q whose R has a positive diagonal, unit 2-norm, largest component real and positive
+ * (LAPACK, which the reference calls, fixes neither the signs of R's diagonal nor the sign of a real eigenvector;
+ * vals, relres and the residues up to that sign/phase do not depend on either); relres_out: d doubles;
+ * residues_out: N x d complex, column-major, interleaved, or NULL. */
+int32_t isokann_residual_ritz(isokann_ctx *ctx, double *vals_out, double *vecs_out, double *relres_out,
+                              double *residues_out);
 /* randperm(rng::Xoshiro, n) of Julia's Random stdlib (the draw Flux.DataLoader(shuffle=true) makes once per epoch,
  * src/iso.jl:181): Xoshiro256++ state in/out (s0..s3 of the Xoshiro struct / task-local RNG), 1-based permutation
  * out.  Host-side (the algorithm is inherently sequential).  UNPINNED against a real Julia session. */
@@ -245,6 +269,17 @@ void *isokann_stream(isokann_ctx *ctx);
 /* host-side small dense algebra used by the N-D targets, exposed for CPU tests:
  * real Schur vectors of a d x d float matrix (column-major in/out), LAPACK sgees conventions */
 int32_t isokann_host_schur(const float *a_colmajor, int32_t d, float *z_colmajor, float *t_colmajor);
+/* ... and by the diagnostics: principal logarithm of a real n x n matrix (n <= 9, column-major doubles), and
+ * eigenvalues / right eigenvectors of a real d x d matrix (d <= 8) in LAPACK's dgeev order and normalisation
+ * (vals: d x (re, im); vecs: d x d complex column-major interleaved, largest component real and positive) */
+int32_t isokann_host_logm(const double *a_colmajor, int32_t n, double *out_colmajor);
+/* the d x d part of the three diagnostics as a function of the second moments uu = sum u u', vu = sum v u' of
+ * u = [chi, 1], v = [Kchi, 1] (row-major (d+1) x (d+1) doubles), so that CPU tests reach it without a device.
+ * what = 0 (rates): out = [n, Q (n x n row-major)];  what = 1 (residual_subspace): out = [A, B] (d x d row-major
+ * each; res = A Kchi - B chi per record);  what = 2 (residual_ritz): out = [vals (d x (re, im)), vecs (d x d complex
+ * column-major interleaved), Are, Bre, Aim, Bim (d x d row-major each), any_complex]. */
+int32_t isokann_host_diag(int32_t what, const double *uu, const double *vu, int32_t d, double *out);
+int32_t isokann_host_eig(const double *a_colmajor, int32_t d, double *vals_reim, double *vecs_reim_colmajor);
 
 #ifdef __cplusplus
 }

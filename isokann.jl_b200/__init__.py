@@ -11,7 +11,7 @@ PyTorch fallback: without the built library and a CUDA device every compute call
 from .data import (ExternalSimulation, FeaturesAll, FeaturesAtoms, FeaturesCoords, FeaturesPairs, SimulationData,
                    coords, features, flatpairdists, pdists, propcoords, propfeatures)
 from .engine import DomainError, Engine, IsokannError
-from .iso import (Iso, addcoords_, cutoff_, propchis, chi_kchi, chicoords, chis, cpu, dchidfeat, dchidx, defaultmodel, draw_perm, isotarget, koopman, load_state, run_, validationloss,
+from .iso import (Iso, addcoords_, cutoff_, propchis, chi_kchi, chicoords, chis, cpu, dchidfeat, dchidx, defaultmodel, draw_perm, isotarget, koopman, load_state, run_, validationloss, rates, residual_subspace, residual_ritz,
                   save, train_batch_)
 from .isotarget import TransformISA, TransformPseudoInv, TransformShiftscale
 from .models import (AdamRegularized, Chain, NesterovRegularized, OptimiserRule, densenet, inputdim, outputdim, pairnet,

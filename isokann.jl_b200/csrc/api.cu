@@ -1653,6 +1653,50 @@ void build_pair_table(Ctx &c) {
   }
 }
 
+// ---- diagnostics on the resident data (loggers) --------------------------------------------------
+// chi = chis(iso) and Kchi = koopman(iso) on the resident data (both N x d on every rank), then the second moments
+// of u = [chi, 1] and v = [Kchi, 1]: uu = sum u u', vu = sum v u', vv = sum v v' (row-major (d+1) x (d+1), fp64)
+struct Moments {
+  double uu[(kMaxD + 1) * (kMaxD + 1)], vu[(kMaxD + 1) * (kMaxD + 1)], vv[(kMaxD + 1) * (kMaxD + 1)];
+};
+
+void diag_moments(Ctx &c, Moments &mo) {
+  IK_REQUIRE(c.d >= 1 && c.d <= kMaxD, ISOKANN_BAD_ARGUMENT, "chi dimension exceeds ISOKANN_MAX_D");
+  compute_chis(c);
+  compute_koopman(c);
+  const int d = c.d, e = d + 1;
+  c.diag_part.ensure((size_t)256 * 3 * (kMaxD + 1) * (kMaxD + 1));
+  int nb = 0;
+  launch_moments(c, c.chi_x.p, c.kchi.p, c.N, d, c.diag_part.p, &nb);
+  double *part = read_back(c, c.diag_part.p, (size_t)nb * e * 3 * e);
+  for (int i = 0; i < e * e; ++i) mo.uu[i] = mo.vu[i] = mo.vv[i] = 0.0;
+  for (int b = 0; b < nb; ++b)
+    for (int a = 0; a < e; ++a)
+      for (int k = 0; k < e; ++k) {
+        const double *q = part + (((size_t)b * e + a) * 3) * e + k;
+        mo.uu[a * e + k] += q[0];
+        mo.vu[a * e + k] += q[e];
+        mo.vv[a * e + k] += q[2 * e];
+      }
+  for (int i = 0; i < e * e; ++i)
+    IK_REQUIRE(std::isfinite(mo.uu[i]) && std::isfinite(mo.vu[i]) && std::isfinite(mo.vv[i]), ISOKANN_BAD_ARGUMENT,
+               "chi or Kchi is not finite");
+}
+
+// one pass r = A Kchi - B chi over the resident data: column sums of r^2 and of (A Kchi)^2, optional N x d output
+void diag_resid_pass(Ctx &c, const Mat8 &A, const Mat8 &B, double *dev_out, double *sum_r2, double *sum_k2) {
+  const int d = c.d;
+  int nb = 0;
+  launch_resid(c, c.kchi.p, c.chi_x.p, c.N, d, A, B, dev_out, c.diag_part.p, &nb);
+  double *part = read_back(c, c.diag_part.p, (size_t)nb * d * 2);
+  for (int j = 0; j < d; ++j) sum_r2[j] = sum_k2[j] = 0.0;
+  for (int b = 0; b < nb; ++b)
+    for (int j = 0; j < d; ++j) {
+      sum_r2[j] += part[((size_t)b * d + j) * 2];
+      sum_k2[j] += part[((size_t)b * d + j) * 2 + 1];
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1809,6 +1853,8 @@ int32_t isokann_destroy(isokann_ctx *c) {
                          &c->delta_a, &c->delta_b, &c->splitk, &c->staging_in, &c->staging_out, &c->red_f,
                          &c->xs_stage, &c->val_chi, &c->val_k1, &c->beta_dev};
   c->staging_f64.release();
+  c->diag_part.release();
+  c->diag_out.release();
   for (auto *b : fb) b->release();
   if (c->tcs) {
     for (auto &b : c->tcs->act) b.release();
@@ -2306,6 +2352,94 @@ int32_t isokann_validationloss(isokann_ctx *c, const float *vxs, const float *vy
   });
 }
 
+int32_t isokann_rates(isokann_ctx *c, double *q_colmajor, int32_t *dim_out) {
+  return guarded(c, [&] {
+    IK_REQUIRE(q_colmajor != nullptr, ISOKANN_BAD_ARGUMENT, "NULL output");
+    Ctx &x = *c;
+    Moments mo;
+    diag_moments(x, mo);
+    double L[kMaxD * kMaxD];
+    int n = 0;
+    const int rc = diag_rates(mo.uu, mo.vu, x.d, L, &n);
+    IK_REQUIRE(rc != 1, ISOKANN_DOMAIN_PINV, "rates: chi chi' is singular (collapsed chi)");
+    IK_REQUIRE(rc == 0, ISOKANN_BAD_ARGUMENT,
+               "rates: Kchi/chi has no real logarithm (an eigenvalue on the closed negative real axis)");
+    for (int a = 0; a < n; ++a)
+      for (int b = 0; b < n; ++b) q_colmajor[a + b * n] = L[a * n + b];
+    if (dim_out) *dim_out = n;
+  });
+}
+
+int32_t isokann_residual_subspace(isokann_ctx *c, int32_t v_norms, double *relres_out, double *res_out) {
+  return guarded(c, [&] {
+    IK_REQUIRE(relres_out != nullptr, ISOKANN_BAD_ARGUMENT, "NULL output");
+    Ctx &x = *c;
+    Moments mo;
+    diag_moments(x, mo);
+    const int d = x.d, e = d + 1;
+    Mat8 A{}, B{};
+    IK_REQUIRE(diag_subspace(mo.uu, mo.vu, d, A, B), ISOKANN_DOMAIN_PINV,
+               "residual_subspace: chi has linearly dependent rows");
+    double *dev_out = nullptr;
+    if (res_out) {
+      x.diag_out.ensure((size_t)x.N * d);
+      dev_out = x.diag_out.p;
+    }
+    double r2[kMaxD], k2[kMaxD];
+    diag_resid_pass(x, A, B, dev_out, r2, k2);
+    for (int j = 0; j < d; ++j) {
+      const double den = v_norms ? mo.uu[j * e + j] : mo.vv[j * e + j];
+      relres_out[j] = std::sqrt(r2[j]) / std::sqrt(den);
+    }
+    if (res_out) {
+      IK_CUDA(cudaMemcpyAsync(res_out, dev_out, (size_t)x.N * d * sizeof(double), cudaMemcpyDeviceToHost, x.stream));
+      sync_stream(x);
+    }
+  });
+}
+
+int32_t isokann_residual_ritz(isokann_ctx *c, double *vals_out, double *vecs_out, double *relres_out,
+                              double *residues_out) {
+  return guarded(c, [&] {
+    IK_REQUIRE(vals_out != nullptr && relres_out != nullptr, ISOKANN_BAD_ARGUMENT, "NULL output");
+    Ctx &x = *c;
+    Moments mo;
+    diag_moments(x, mo);
+    const int d = x.d;
+    bool any_complex = false;
+    Mat8 Are{}, Bre{}, Aim{}, Bim{};
+    IK_REQUIRE(diag_ritz(mo.uu, mo.vu, d, vals_out, vecs_out, Are, Bre, Aim, Bim, &any_complex), ISOKANN_DOMAIN_PINV,
+               "residual_ritz: chi has linearly dependent rows or eigen(Kr) failed");
+    double *dev_re = nullptr, *dev_im = nullptr;
+    if (residues_out) {
+      x.diag_out.ensure((size_t)x.N * d * 2);
+      dev_re = x.diag_out.p;
+      dev_im = x.diag_out.p + (size_t)x.N * d;
+    }
+    double r2[kMaxD], k2[kMaxD], r2i[kMaxD], k2i[kMaxD];
+    diag_resid_pass(x, Are, Bre, dev_re, r2, k2);
+    for (int j = 0; j < d; ++j) r2i[j] = k2i[j] = 0.0;
+    if (any_complex) diag_resid_pass(x, Aim, Bim, dev_im, r2i, k2i);
+    for (int j = 0; j < d; ++j) relres_out[j] = std::sqrt(r2[j] + r2i[j]) / std::sqrt(k2[j] + k2i[j]);
+    if (residues_out) {  // interleave (re, im) like a Julia Matrix{ComplexF64}, in pieces through the pinned buffer
+      const size_t total = (size_t)x.N * d, piece = (size_t)1 << 20;
+      for (size_t o = 0; o < total; o += piece) {
+        const size_t m = std::min(piece, total - o);
+        ensure_pinned(x, 2 * m * sizeof(double));
+        double *h = reinterpret_cast<double *>(x.pinned);
+        IK_CUDA(cudaMemcpyAsync(h, dev_re + o, m * sizeof(double), cudaMemcpyDeviceToHost, x.stream));
+        if (any_complex)
+          IK_CUDA(cudaMemcpyAsync(h + m, dev_im + o, m * sizeof(double), cudaMemcpyDeviceToHost, x.stream));
+        sync_stream(x);
+        for (size_t i = 0; i < m; ++i) {
+          residues_out[2 * (o + i)] = h[i];
+          residues_out[2 * (o + i) + 1] = any_complex ? h[m + i] : 0.0;
+        }
+      }
+    }
+  });
+}
+
 // Julia's randperm(rng::Xoshiro, n) replayed on the host (Random stdlib, Julia 1.12): Xoshiro256++ draws, the 52-bit
 // raw sample `rand(UInt64) >>> 12`, and randperm!'s inside-out shuffle with ltm52's masked rejection sampling
 // ("minibatch order").  UNPINNED: no golden vector from a Julia session is available in this environment;
@@ -2462,6 +2596,69 @@ int32_t isokann_release_host_buffers(isokann_ctx *c) {
     sync_stream(*c);
     release_host_registrations(*c);
   });
+}
+
+int32_t isokann_host_diag(int32_t what, const double *uu, const double *vu, int32_t d, double *out) {
+  if (!uu || !vu || !out || d < 1 || d > ik::kMaxD) return ISOKANN_BAD_ARGUMENT;
+  const int dd = d * d;
+  if (what == 0) {
+    int n = 0;
+    const int rc = ik::diag_rates(uu, vu, d, out + 1, &n);
+    out[0] = (double)n;
+    return rc == 0 ? ISOKANN_OK : (rc == 1 ? ISOKANN_DOMAIN_PINV : ISOKANN_BAD_ARGUMENT);
+  }
+  if (what == 1) {
+    ik::Mat8 A{}, B{};
+    if (!ik::diag_subspace(uu, vu, d, A, B)) return ISOKANN_DOMAIN_PINV;
+    for (int i = 0; i < dd; ++i) {
+      out[i] = A.m[i];
+      out[dd + i] = B.m[i];
+    }
+    return ISOKANN_OK;
+  }
+  if (what == 2) {
+    ik::Mat8 Are{}, Bre{}, Aim{}, Bim{};
+    bool any_complex = false;
+    if (!ik::diag_ritz(uu, vu, d, out, out + 2 * d, Are, Bre, Aim, Bim, &any_complex)) return ISOKANN_DOMAIN_PINV;
+    double *q = out + 2 * d + 2 * dd;
+    for (int i = 0; i < dd; ++i) {
+      q[i] = Are.m[i];
+      q[dd + i] = Bre.m[i];
+      q[2 * dd + i] = Aim.m[i];
+      q[3 * dd + i] = Bim.m[i];
+    }
+    q[4 * dd] = any_complex ? 1.0 : 0.0;
+    return ISOKANN_OK;
+  }
+  return ISOKANN_BAD_ARGUMENT;
+}
+
+int32_t isokann_host_logm(const double *a_colmajor, int32_t n, double *out_colmajor) {
+  if (!a_colmajor || !out_colmajor || n < 1 || n > ik::kMaxD + 1) return ISOKANN_BAD_ARGUMENT;
+  double a[(ik::kMaxD + 1) * (ik::kMaxD + 1)], l[(ik::kMaxD + 1) * (ik::kMaxD + 1)];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) a[i * n + j] = a_colmajor[i + j * n];
+  if (!ik::host_logm(a, n, l)) return ISOKANN_BAD_ARGUMENT;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) out_colmajor[i + j * n] = l[i * n + j];
+  return ISOKANN_OK;
+}
+
+int32_t isokann_host_eig(const double *a_colmajor, int32_t n, double *vals_reim, double *vecs_reim_colmajor) {
+  if (!a_colmajor || !vals_reim || !vecs_reim_colmajor || n < 1 || n > ik::kMaxD) return ISOKANN_BAD_ARGUMENT;
+  double a[ik::kMaxD * ik::kMaxD], wr[ik::kMaxD], wi[ik::kMaxD], vre[ik::kMaxD * ik::kMaxD], vim[ik::kMaxD * ik::kMaxD];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) a[i * n + j] = a_colmajor[i + j * n];
+  if (!ik::host_eig_general(a, n, wr, wi, vre, vim)) return ISOKANN_BAD_ARGUMENT;
+  for (int j = 0; j < n; ++j) {
+    vals_reim[2 * j] = wr[j];
+    vals_reim[2 * j + 1] = wi[j];
+    for (int i = 0; i < n; ++i) {
+      vecs_reim_colmajor[2 * (i + j * n)] = vre[i * n + j];
+      vecs_reim_colmajor[2 * (i + j * n) + 1] = vim[i * n + j];
+    }
+  }
+  return ISOKANN_OK;
 }
 
 int32_t isokann_host_schur(const float *a_colmajor, int32_t d, float *z_colmajor, float *t_colmajor) {

@@ -146,6 +146,9 @@ void launch_f64_to_f32(Ctx &c, const double *in, int64_t n, float *out);
 void launch_valloss(Ctx &c, const float *chi, const float *k1, int64_t n, float mn, float mx, double *partials,
                     int *nblocks_out);
 void launch_gram(Ctx &c, const float *chi, const float *kchi, int64_t n, int d, double *partials, int *nblocks_out);
+void launch_moments(Ctx &c, const float *chi, const float *kchi, int64_t n, int d, double *partials, int *nblocks_out);
+void launch_resid(Ctx &c, const float *kchi, const float *chi, int64_t n, int d, const Mat8 &A, const Mat8 &B,
+                  double *out_colmajor, double *partials, int *nblocks_out);
 void launch_apply(Ctx &c, int mode, const float *kchi, const float *chi, int64_t n, int d, const Mat8 &mat,
                   float *target_out, double *partials, int *nblocks_out);
 void launch_isa_argmax(Ctx &c, const float *kchi, int64_t n, const IsaReplay &rp, ArgmaxPartial *partials,
@@ -175,6 +178,16 @@ double isa_row_norm_host(const float *row, const IsaReplay &rp, double *xout);
 bool host_inverse(const double *a_rowmajor, int d, double *inv_rowmajor);
 void host_sym_eig(const double *a_rowmajor, int d, double *evals, double *evecs_rowmajor);
 bool host_schur_f32(const float *a_colmajor, int d, float *z_colmajor, float *t_colmajor);
+bool host_schur_f64(const double *a_colmajor, int d, double *z_colmajor, double *t_colmajor);
+// diagnostics (hostdiag.cpp): principal matrix logarithm (n <= kMaxD + 1), upper Cholesky factor, general eigenproblem
+bool host_logm(const double *a_rowmajor, int n, double *out_rowmajor);
+bool host_cholesky_upper(const double *g_rowmajor, int n, double *r_rowmajor);
+bool host_eig_general(const double *a_rowmajor, int n, double *wr, double *wi, double *vre_rowmajor,
+                      double *vim_rowmajor);
+int diag_rates(const double *uu, const double *vu, int d, double *q_rowmajor, int *n_out);
+bool diag_subspace(const double *uu, const double *vu, int d, Mat8 &A, Mat8 &B);
+bool diag_ritz(const double *uu, const double *vu, int d, double *vals, double *vecs, Mat8 &Are, Mat8 &Bre, Mat8 &Aim,
+               Mat8 &Bim, bool *any_complex);
 
 // dynamically loaded NCCL (nccl_dyn.cpp)
 struct Nccl;
@@ -278,6 +291,7 @@ struct Ctx {
   std::vector<DevBuf<float>> act;  // act[l]: rows x widths[l]
   DevBuf<float> delta_a, delta_b, splitk, staging_in, staging_out, red_f;
   DevBuf<double> red_d, epoch_loss, staging_f64;
+  DevBuf<double> diag_part, diag_out;  // diagnostics (rates, residual_*): block partials, N x d residual matrix
   DevBuf<ArgmaxPartial> red_am;
   DevBuf<int64_t> perm_dev, perm_raw;
   DevBuf<int> flags;

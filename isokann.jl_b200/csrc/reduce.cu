@@ -206,6 +206,88 @@ void launch_gram(Ctx &c, const float *chi, const float *kchi, int64_t n, int d, 
   *nblocks_out = gx;
 }
 
+// ---- second moments of the augmented rows u = [chi[n,:], 1], v = [kchi[n,:], 1] for the diagnostics (rates:
+//      src/iso.jl:339-351, residual_ritz/subspace: src/isotarget.jl:787-821).  With e = d + 1, per block and row a:
+//      partial[((blk*e + a)*3 + 0)*e + b] = sum_n u_a u_b     (chi chi', column sums of chi, N)
+//      partial[((blk*e + a)*3 + 1)*e + b] = sum_n v_a u_b     (Kchi chi')
+//      partial[((blk*e + a)*3 + 2)*e + b] = sum_n v_a v_b     (Kchi Kchi')                         (fp64) ----
+__global__ void moments_kernel(const float *__restrict__ chi, const float *__restrict__ kchi, int64_t n, int d,
+                               double *__restrict__ partials) {
+  constexpr int E = kMaxD + 1;
+  const int a = blockIdx.y, e = d + 1;
+  double acc[3 * E];
+#pragma unroll
+  for (int b = 0; b < 3 * E; ++b) acc[b] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ua = a < d ? (double)chi[i * d + a] : 1.0;
+    const double va = a < d ? (double)kchi[i * d + a] : 1.0;
+#pragma unroll
+    for (int b = 0; b < E; ++b) {
+      if (b < e) {
+        const double ub = b < d ? (double)chi[i * d + b] : 1.0;
+        const double vb = b < d ? (double)kchi[i * d + b] : 1.0;
+        acc[b] += ua * ub;
+        acc[E + b] += va * ub;
+        acc[2 * E + b] += va * vb;
+      }
+    }
+  }
+  for (int k = 0; k < 3; ++k)
+    for (int b = 0; b < e; ++b) {
+      const double s = block_sum_d(acc[k * E + b]);
+      if (threadIdx.x == 0) partials[(((int64_t)blockIdx.x * e + a) * 3 + k) * e + b] = s;
+    }
+}
+
+void launch_moments(Ctx &c, const float *chi, const float *kchi, int64_t n, int d, double *partials, int *nblocks_out) {
+  int gx = red_grid(c, n);
+  if (gx > 256) gx = 256;
+  dim3 grid(gx, d + 1);
+  moments_kernel<<<grid, kRedThreads, 0, c.stream>>>(chi, kchi, n, d, partials);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_REDUCE);
+  *nblocks_out = gx;
+}
+
+// ---- residual matrices of the diagnostics: r[n,j] = sum_b A[j,b] kchi[n,b] - sum_b B[j,b] chi[n,b]   (fp64)
+//      out (optional): N x d column-major doubles, as Julia holds `res` / `residues`
+//      partial[(blk*d + j)*2 + {0,1}] = sum_n r[n,j]^2, sum_n (sum_b A[j,b] kchi[n,b])^2
+__global__ void resid_kernel(const float *__restrict__ kchi, const float *__restrict__ chi, int64_t n, int d, Mat8 A,
+                             Mat8 B, double *__restrict__ out, double *__restrict__ partials) {
+  const int j = blockIdx.y;
+  double s_r = 0.0, s_k = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double tk = 0.0, tv = 0.0;
+#pragma unroll
+    for (int b = 0; b < kMaxD; ++b)
+      if (b < d) {
+        tk += A.m[j * d + b] * (double)kchi[i * d + b];
+        tv += B.m[j * d + b] * (double)chi[i * d + b];
+      }
+    const double r = tk - tv;
+    if (out) out[(int64_t)j * n + i] = r;
+    s_r += r * r;
+    s_k += tk * tk;
+  }
+  const double t0 = block_sum_d(s_r);
+  const double t1 = block_sum_d(s_k);
+  if (threadIdx.x == 0) {
+    partials[((int64_t)blockIdx.x * d + j) * 2] = t0;
+    partials[((int64_t)blockIdx.x * d + j) * 2 + 1] = t1;
+  }
+}
+
+void launch_resid(Ctx &c, const float *kchi, const float *chi, int64_t n, int d, const Mat8 &A, const Mat8 &B,
+                  double *out_colmajor, double *partials, int *nblocks_out) {
+  int gx = red_grid(c, n);
+  if (gx > 256) gx = 256;
+  dim3 grid(gx, d);
+  resid_kernel<<<grid, kRedThreads, 0, c.stream>>>(kchi, chi, n, d, A, B, out_colmajor, partials);
+  IK_CUDA(cudaGetLastError());
+  c.count_launch(KC_REDUCE);
+  *nblocks_out = gx;
+}
+
 // ---- t[n,a] = sum_b mat[a,b] * kchi[n,b] with three consumers:
 //   mode 0 (L1)   : partial[blk*d + a]       = sum_n |t[n,a]|
 //   mode 1 (COST) : partial[(blk*d + a)*d+b] = sum_n |t[n,a] - chi[n,b]|        (fixperm cost matrix)

@@ -287,6 +287,32 @@ class Engine:
         self._check(self.lib.isokann_validationloss(self.h, L.ptr(vxs), L.ptr(vys), D, K, Nv, C.byref(out)))
         return out.value
 
+    def rates(self) -> np.ndarray:
+        """rates(iso) * lagtime (src/iso.jl:339-351): log(Kchi / chi) on the resident data, (dim, dim) float64"""
+        q = np.zeros(64, dtype=np.float64)
+        dim = C.c_int32()
+        self._check(self.lib.isokann_rates(self.h, L.ptr(q), C.byref(dim)))
+        n = dim.value
+        return q[:n * n].reshape(n, n, order="F").copy()
+
+    def residual_subspace(self, v_norms: bool = False, want_res: bool = False):
+        """residual_subspace(iso) (src/isotarget.jl:805-821) -> (res (N, d) float64 or None, relres (d,))"""
+        d, N = self.d, self.N
+        relres = np.zeros(d, dtype=np.float64)
+        res = np.zeros((N, d), dtype=np.float64, order="F") if want_res else None
+        self._check(self.lib.isokann_residual_subspace(self.h, 1 if v_norms else 0, L.ptr(relres), L.ptr(res)))
+        return res, relres
+
+    def residual_ritz(self, want_residues: bool = False):
+        """residual_ritz(iso) (src/isotarget.jl:787-802) -> dict(residues, relres, vals, vecs); complex128 arrays"""
+        d, N = self.d, self.N
+        vals = np.zeros(d, dtype=np.complex128)
+        vecs = np.zeros((d, d), dtype=np.complex128, order="F")
+        relres = np.zeros(d, dtype=np.float64)
+        residues = np.zeros((N, d), dtype=np.complex128, order="F") if want_residues else None
+        self._check(self.lib.isokann_residual_ritz(self.h, L.ptr(vals), L.ptr(vecs), L.ptr(relres), L.ptr(residues)))
+        return {"residues": residues, "relres": relres, "vals": vals, "vecs": vecs}
+
     @staticmethod
     def randperm(state4, n: int):
         """Julia's randperm(Xoshiro(s0, s1, s2, s3), n): returns (1-based permutation, advanced state)"""

@@ -164,6 +164,25 @@ def validationloss(iso: Iso, valdata: SimulationData) -> float:
     return iso.engine.validationloss(vx, vy)     # one library call, only the scalar comes back
 
 
+def rates(iso: Iso, lagtime: float = 1.0) -> np.ndarray:
+    """rates(iso) (src/iso.jl:339-343): the coarse-grained rate matrix Q with K chi = exp(tau Q) chi; for one dimensional
+    chi the rates of chi and 1 - chi.  lagtime = lagtime(iso.data.sim) (the host simulation object knows it).
+    One library call (isokann_rates); chi and K chi never leave the device."""
+    return iso.engine.rates() / float(lagtime)
+
+
+def residual_subspace(iso: Iso, v_norms: bool = False, want_res: bool = False):
+    """residual_subspace(iso) (src/isotarget.jl:805-821): how badly each K chi_j is represented in span(chi).
+    Returns (res, relres) like the reference's named tuple; res only on request (it is N x d)."""
+    return iso.engine.residual_subspace(v_norms, want_res)
+
+
+def residual_ritz(iso: Iso, want_residues: bool = False) -> dict:
+    """residual_ritz(iso) (src/isotarget.jl:787-802): Ritz values/vectors of the Koopman operator on span(chi) and
+    their relative residuals (isokann_residual_ritz)"""
+    return iso.engine.residual_ritz(want_residues)
+
+
 def koopman(iso: Iso) -> np.ndarray:
     """koopman(iso) = expectation(model, propfeatures(data)) (src/isotarget.jl:20)"""
     return iso.engine.koopman()
@@ -202,6 +221,6 @@ def load_state(path: str, iso: Iso) -> Iso:
     return iso
 
 
-__all__ = ["Iso", "validationloss", "dchidx", "dchidfeat", "addcoords_", "cutoff_", "propchis", "run_", "train_batch_", "isotarget", "chis", "chicoords", "koopman", "chi_kchi", "cpu", "save",
+__all__ = ["Iso", "validationloss", "rates", "residual_subspace", "residual_ritz", "dchidx", "dchidfeat", "addcoords_", "cutoff_", "propchis", "run_", "train_batch_", "isotarget", "chis", "chicoords", "koopman", "chi_kchi", "cpu", "save",
            "load_state", "defaultmodel", "draw_perm", "DomainError", "TransformShiftscale", "TransformISA",
            "TransformPseudoInv"]

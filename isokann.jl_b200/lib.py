@@ -102,6 +102,9 @@ SIGNATURES = {
     "isokann_target": (C.c_int32, [_p, C.c_int32, C.POINTER(TargetOpts), _p]),
     "isokann_download_target": (C.c_int32, [_p, _p]),
     "isokann_validationloss": (C.c_int32, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64, _d]),
+    "isokann_rates": (C.c_int32, [_p, _p, C.POINTER(C.c_int32)]),
+    "isokann_residual_subspace": (C.c_int32, [_p, C.c_int32, _p, _p]),
+    "isokann_residual_ritz": (C.c_int32, [_p, _p, _p, _p, _p]),
     "isokann_randperm": (C.c_int32, [_p, C.c_int64, _p]),
     "isokann_set_target": (C.c_int32, [_p, _p, C.c_int64, C.c_int64]),
     "isokann_train_epoch": (C.c_int32, [_p, _p, C.c_int64, C.c_int32, _d]),
@@ -114,6 +117,9 @@ SIGNATURES = {
     "isokann_synchronize": (C.c_int32, [_p]),
     "isokann_stream": (_p, [_p]),
     "isokann_host_schur": (C.c_int32, [_p, C.c_int32, _p, _p]),
+    "isokann_host_logm": (C.c_int32, [_p, C.c_int32, _p]),
+    "isokann_host_diag": (C.c_int32, [C.c_int32, _p, _p, C.c_int32, _p]),
+    "isokann_host_eig": (C.c_int32, [_p, C.c_int32, _p, _p]),
 }
 
 _lib = None

@@ -1,4 +1,4 @@
-# ISOKANNB200.jl -- the reference-side binding of libisokann_b200.so (include/isokann_b200.h, ABI version 2).
+# ISOKANNB200.jl -- the reference-side binding of libisokann_b200.so (include/isokann_b200.h, ABI version 3).
 #
 # Load it next to ISOKANN.jl (`include("ISOKANNB200.jl"); using .ISOKANNB200`) with ENV["ISOKANN_B200_LIB"]
 # pointing at the built library.  It adds *methods* to the reference's own generic functions, dispatching on a
@@ -15,6 +15,8 @@
 #   isotarget(t, model, xs, ys)            src/isotarget.jl:34,100,152     isokann_target  (target stays resident)
 #   train_batch!(model, xs, ys, opt, mb)   src/iso.jl:179-194              isokann_train_epoch
 #   chis / chicoords / dchidx / addcoords! src/iso.jl:203,211,238          isokann_chis / _forward / _chi_vjp / _append_data
+#   validationloss / rates                 src/iso.jl:160-168,339-351      isokann_validationloss / _rates
+#   residual_ritz / residual_subspace      src/isotarget.jl:787-821        isokann_residual_ritz / _residual_subspace
 #
 # STATUS: written against the reference sources and Optimisers.jl 0.4 / Flux 0.16 state-tree layout, but NOT
 # EXECUTED in the build environment (there is no Julia there).  The Python ctypes mirror (isokann.jl_b200/lib.py,
@@ -323,6 +325,42 @@ function ISOKANN.validationloss(iso::Iso{<:B200Model}, valdata::SimulationData)
         (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64, Int64, Int64, Ref{Float64}),
         iso.model.handle, vx, vy, D, K, Nv, out))
     out[]
+end
+
+# rates(iso) (src/iso.jl:339-343): log(Kchi / chi) / lagtime; chi and Kchi stay on the device
+function ISOKANN.rates(iso::Iso{<:B200Model})
+    n = max(ISOKANN.outputdim(iso.model.chain), 2)
+    q = Matrix{Float64}(undef, n, n)
+    check(iso.model, ccall((:isokann_rates, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}), iso.model.handle, q, C_NULL))
+    q ./ ISOKANN.lagtime(iso.data.sim)
+end
+
+# residual_subspace(iso) (src/isotarget.jl:805-821) on the resident data; `res=false` returns only relres (d numbers)
+function ISOKANN.residual_subspace(iso::Iso{<:B200Model}; V_norms=false, res=true)
+    m = iso.model
+    d = ISOKANN.outputdim(m.chain)
+    relres = Vector{Float64}(undef, d)
+    R = res ? Matrix{Float64}(undef, m.N, d) : nothing
+    check(m, ccall((:isokann_residual_subspace, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}),
+        m.handle, V_norms, relres, res ? R : C_NULL))
+    (; res=R, relres)
+end
+
+# residual_ritz(iso) (src/isotarget.jl:787-802); vecs are given in the basis Q whose R has a positive diagonal
+# (Q = V / R with R = cholesky(V'V).U), which is what the returned named tuple's Q would be -- form it on the host if
+# needed; `residues=false` returns only the O(d^2) quantities
+function ISOKANN.residual_ritz(iso::Iso{<:B200Model}; residues=true)
+    m = iso.model
+    d = ISOKANN.outputdim(m.chain)
+    vals = Vector{ComplexF64}(undef, d); vecs = Matrix{ComplexF64}(undef, d, d); relres = Vector{Float64}(undef, d)
+    R = residues ? Matrix{ComplexF64}(undef, m.N, d) : nothing
+    check(m, ccall((:isokann_residual_ritz, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Float64}, Ptr{ComplexF64}),
+        m.handle, vals, vecs, relres, residues ? R : C_NULL))
+    if all(iszero ∘ imag, vals)      # a real spectrum gives real results in the reference
+        return (; residues=residues ? real.(R) : nothing, relres, vals=real.(vals), vecs=real.(vecs))
+    end
+    (; residues=R, relres, vals, vecs)
 end
 
 # addcoords!(iso, coords) (src/iso.jl:238): propagate on the host as before, upload only the new block

@@ -31,6 +31,7 @@ __all__ = [
     "isotarget_pinv", "isotarget", "isa_from_chi", "pinv_from_chi", "OptConfig", "OptState", "opt_init",
     "opt_update", "loss_weights", "batch_loss_and_grad", "train_batch",
     "run", "weighted_expectation", "chi_vjp", "xoshiro256pp_next", "julia_randperm",
+    "rates", "residual_subspace", "residual_ritz",
 ]
 
 F32 = np.float32
@@ -719,3 +720,55 @@ def chi_vjp(m: Model, x: np.ndarray, cot: Optional[np.ndarray] = None, pairs0: O
     np.add.at(out, (np.arange(M)[:, None], pairs0[None, :, 0]), contrib)
     np.add.at(out, (np.arange(M)[:, None], pairs0[None, :, 1]), -contrib)
     return out.reshape(M, -1)
+
+
+# ----------------------------------------------------------------------------------------------
+# diagnostics ("next" row 4): rates (src/iso.jl:339-351), residual_subspace
+# (src/isotarget.jl:805-821), residual_ritz (src/isotarget.jl:787-802).  chi, kchi: (N, d) records,
+# i.e. already the V = chis(iso)' and KV = koopman(iso)' of the reference.
+# ----------------------------------------------------------------------------------------------
+
+def rates(chi: np.ndarray, kchi: np.ndarray, dtype=F64) -> np.ndarray:
+    """rates(x, y) = log(y / x) with x = chi (d x N), y = Kchi, src/iso.jl:345-351 (no division by the lag time).
+    `y / x` is Julia's right division = the least-squares solution M of M x = y (LAPACK QR), here numpy lstsq;
+    `log` is the principal matrix logarithm (scipy.linalg.logm).  The reference runs this in Float32
+    (dtype=np.float32 reproduces that up to LAPACK's rounding); returns the Julia-shaped (dim, dim) matrix."""
+    import scipy.linalg
+    x = np.asarray(chi, dtype=dtype).T                      # d x N
+    y = np.asarray(kchi, dtype=dtype).T
+    if x.shape[0] == 1:                                     # src/iso.jl:346-349
+        x = np.concatenate([x, 1 - x], axis=0)
+        y = np.concatenate([y, 1 - y], axis=0)
+    m = np.linalg.lstsq(x.T, y.T, rcond=None)[0].T          # y / x
+    return scipy.linalg.logm(m)
+
+
+def _qr_thin(V: np.ndarray):
+    return np.linalg.qr(V, mode="reduced")                  # qr_thin, src/isotarget.jl:823
+
+
+def residual_subspace(chi: np.ndarray, kchi: np.ndarray, v_norms: bool = False):
+    """src/isotarget.jl:810-821: res = KV - Q Q' KV, relres = column norms relative to KV (or V).  Float64."""
+    V = np.asarray(chi, dtype=F64)
+    KV = np.asarray(kchi, dtype=F64)
+    Q, _ = _qr_thin(V)
+    res = KV - Q @ (Q.T @ KV)
+    den = np.linalg.norm(V, axis=0) if v_norms else np.linalg.norm(KV, axis=0)
+    return res, np.linalg.norm(res, axis=0) / den
+
+
+def residual_ritz(chi: np.ndarray, kchi: np.ndarray):
+    """src/isotarget.jl:787-802: Q, R = qr(V); KQ = KV inv(R); Kr = Q' KQ; eigen(Kr, sortby = x -> abs(1 - x));
+    residues = KQ vecs - vals' .* (Q vecs); relres = column norms relative to KQ vecs.
+    Returns (residues, relres, vals, vecs, Q); vals/vecs complex when Kr has complex eigenvalues."""
+    V = np.asarray(chi, dtype=F64)
+    KV = np.asarray(kchi, dtype=F64)
+    Q, R = _qr_thin(V)
+    KQ = KV @ np.linalg.inv(R)
+    Kr = Q.T @ KQ
+    vals, vecs = np.linalg.eig(Kr)                          # LAPACK dgeev, like Julia's eigen
+    order = np.argsort(np.abs(1 - vals), kind="stable")     # sortby (insertion sort for d <= 20: stable)
+    vals, vecs = vals[order], vecs[:, order]
+    residues = KQ @ vecs - vals[None, :] * (Q @ vecs)
+    relres = np.linalg.norm(residues, axis=0) / np.linalg.norm(KQ @ vecs, axis=0)
+    return residues, relres, vals, vecs, Q

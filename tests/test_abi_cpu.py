@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound(pkg):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in pkg.lib.SIGNATURES, f"{n} has no ctypes binding"
-    assert lib.isokann_abi_version() == 2
+    assert lib.isokann_abi_version() == 3
 
 
 def test_struct_layout_matches_header(pkg):

@@ -490,6 +490,51 @@ def test_validationloss(pkg, oracle):
     assert np.isclose(got, np.mean((c - skc) ** 2), rtol=2e-3)
 
 
+@pytest.mark.parametrize("name,kind,N", [("c1", "shiftscale", 300), ("c4", "isa", 700), ("c2", "shiftscale", 5000)])
+def test_rates_and_residuals(pkg, oracle, name, kind, N):
+    """rates (src/iso.jl:339-351), residual_subspace and residual_ritz (src/isotarget.jl:787-821) as
+    device reductions + host d x d algebra, against the oracle's QR-based restatement evaluated on the library's own
+    chi and Kchi (so that exactly the diagnostics are compared; chi parity has its own tests), after a few training
+    iterations so that chi is not the nearly constant function of a random initialisation."""
+    w = pkg.synthetic.WORKLOADS[name]
+    xs, ys = pkg.synthetic.make_data(w, N, 4)
+    om = oracle_model(oracle, w.widths, w.layernorm, w.seed + 1)
+    iso = make_iso(pkg, w, xs, ys, oracle.flatten_params(om), opt="adam", target=kind, minibatch=100)
+    pkg.run_(iso, 4, perms=pkg.synthetic.make_perms(w, N, 4))
+    chi, kchi = records(pkg.chis(iso)), records(pkg.koopman(iso))
+    d = chi.shape[1]
+    # rates: the reference works in Float32, the library (like this oracle call) in Float64
+    q = pkg.rates(iso)
+    q_ref = oracle.rates(chi, kchi)
+    assert q.shape == (max(d, 2),) * 2
+    assert np.abs(q - q_ref.real).max() < 1e-7 * max(1.0, np.abs(q_ref).max()), (q, q_ref)
+    assert np.allclose(pkg.rates(iso, lagtime=0.5), 2 * q)
+    # residual_subspace
+    res, relres = pkg.residual_subspace(iso, want_res=True)
+    res_ref, relres_ref = oracle.residual_subspace(chi, kchi)
+    assert res.shape == (N, d)
+    assert np.abs(res - res_ref).max() < 1e-9 * max(1.0, np.abs(kchi).max())
+    assert np.allclose(relres, relres_ref, rtol=1e-7)
+    res_none, relres_v = pkg.residual_subspace(iso, v_norms=True)
+    assert res_none is None
+    assert np.allclose(relres_v, oracle.residual_subspace(chi, kchi, v_norms=True)[1], rtol=1e-7)
+    # residual_ritz
+    got = pkg.residual_ritz(iso, want_residues=True)
+    residues_ref, rr_ref, vals_ref, vecs_ref, _ = oracle.residual_ritz(chi, kchi)
+    assert np.allclose(got["vals"], vals_ref, atol=1e-8)
+    assert np.allclose(got["relres"], rr_ref, rtol=1e-6)
+    _, R = np.linalg.qr(chi.astype(np.float64))
+    sgn = np.sign(np.diag(R))
+    for j in range(d):                                   # up to the sign of R's diagonal and a unit phase per column
+        v_ref = sgn * vecs_ref[:, j]
+        ph = np.vdot(v_ref, got["vecs"][:, j])
+        ph /= abs(ph)
+        assert np.allclose(got["vecs"][:, j], ph * v_ref, atol=1e-6)
+        assert np.abs(got["residues"][:, j] - ph * residues_ref[:, j]).max() < 1e-7
+    lean = pkg.residual_ritz(iso)                        # without the N x d matrix: only O(d^2) numbers come back
+    assert lean["residues"] is None and np.allclose(lean["relres"], got["relres"], rtol=1e-12)
+
+
 # ---------------------------------------------------------------------------------------------
 # edge cases
 # ---------------------------------------------------------------------------------------------
