@@ -157,11 +157,15 @@ int32_t isokann_set_data_async(isokann_ctx *ctx, const float *xs, const float *y
                                int64_t N, int64_t n_offset, int64_t n_local);
 int32_t isokann_release_host_buffers(isokann_ctx *ctx);
 /* addcoords!(iso, coords) / mergedata (src/simulation.jl:162-185, src/iso.jl:238): append n_new start points and
- * their K Koopman samples to the resident data without re-uploading what is already there (single rank;
- * data must be library-owned).  The resident target becomes invalid, as in the reference where run! recomputes it. */
+ * their K Koopman samples to the resident data without re-uploading what is already there (data must be
+ * library-owned).  The resident target becomes invalid, as in the reference where run! recomputes it.
+ * Several ranks: every rank passes the same complete block; the contiguous split of the grown N moves all shard
+ * boundaries, so the shards of ys are rebuilt on the devices (one all-gather over NVLink, then every rank cuts out
+ * its new range); results equal a fresh isokann_set_data_sharded of the grown data bit for bit. */
 int32_t isokann_append_data(isokann_ctx *ctx, const float *xs_new, const float *ys_new, int64_t D, int64_t K,
                             int64_t n_new);
-/* iso.data = iso.data[end-cutoff+1:end] of run_kde! (src/iso.jl:288-290): keep the newest n_keep start points */
+/* iso.data = iso.data[end-cutoff+1:end] of run_kde! (src/iso.jl:288-290): keep the newest n_keep start points
+ * (several ranks: same n_keep everywhere, shards rebuilt like isokann_append_data) */
 int32_t isokann_keep_last(isokann_ctx *ctx, int64_t n_keep);
 /* model(flattenlast(propfeatures(data))) of resample_kde / chistratcoords (src/simulation.jl:199-207,227-228):
  * chi of every resident Koopman sample, d x K x N, no K-mean */

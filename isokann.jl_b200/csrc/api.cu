@@ -1593,6 +1593,44 @@ void set_data_impl(Ctx &c, const void *xs, const void *ys, bool f64, bool dev_pt
   c.ys = have_ys ? c.ys_own.p : nullptr;
 }
 
+// Incremental data on a multi-rank context (isokann_append_data / isokann_keep_last): rebuild this rank's shard of
+// ys for the new global range.  New start point i (0 <= i < N_new) is the old start point i + shift while
+// i + shift < N_old, else row i + shift - N_old of the appended block (host, the same on every rank).  The contiguous
+// split moves every shard boundary, so rows change owner; the old shards are all-gathered once over NVLink (the same
+// padded collective as the Koopman vector) and every rank cuts its new range out of the gathered copy.  xs is
+// replicated and handled by the caller.
+void reshard_ys(Ctx &c, int64_t N_old, int64_t shift, int64_t N_new, const float *ys_new_host) {
+  const int64_t KD = c.K * c.D;
+  int64_t o1, l1;
+  split_range(N_new, c.world, c.rank, &o1, &l1);
+  if (KD > 0) {
+    IK_REQUIRE(KD <= INT32_MAX, ISOKANN_BAD_ARGUMENT, "K * D too large");
+    DevBuf<float> full, nb;
+    full.ensure((size_t)std::max<int64_t>(1, N_old * KD));
+    allgather_rows(c, c.ys_own.p, c.n_loc, full.p, (int)KD);  // c.N is still N_old here
+    nb.ensure((size_t)std::max<int64_t>(1, l1 * KD));
+    const int64_t a = o1 + shift, b = std::min(o1 + l1 + shift, N_old);  // rows taken from the old data
+    if (b > a)
+      IK_CUDA(cudaMemcpyAsync(nb.p, full.p + a * KD, (size_t)(b - a) * KD * sizeof(float), cudaMemcpyDeviceToDevice,
+                              c.stream));
+    const int64_t a2 = std::max(o1 + shift, N_old), b2 = o1 + l1 + shift;  // rows taken from the appended block
+    if (b2 > a2) {
+      IK_REQUIRE(ys_new_host != nullptr, ISOKANN_BAD_ARGUMENT, "appended Koopman samples missing");
+      IK_CUDA(cudaMemcpyAsync(nb.p + (a2 - shift - o1) * KD, ys_new_host + (a2 - N_old) * KD,
+                              (size_t)(b2 - a2) * KD * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    }
+    sync_stream(c);
+    full.release();
+    c.gather_pad.release();  // it held (world + 1) padded shards of ys; the per-iteration gathers need far less
+    c.ys_own.release();
+    c.ys_own = nb;
+    c.ys = c.ys_own.p;
+  }
+  c.N = N_new;
+  c.n_off = o1;
+  c.n_loc = l1;
+}
+
 void build_pair_table(Ctx &c) {
   const isokann_config &g = c.cfg;
   std::vector<int2> tab;
@@ -1990,7 +2028,6 @@ int32_t isokann_set_data_async(isokann_ctx *c, const float *xs, const float *ys_
 int32_t isokann_append_data(isokann_ctx *c, const float *xs_new, const float *ys_new, int64_t D, int64_t K,
                             int64_t n_new) {
   return guarded(c, [&] {
-    IK_REQUIRE(c->world == 1, ISOKANN_ERR_STATE, "isokann_append_data is single-rank only");
     IK_REQUIRE(c->xs != nullptr && c->xs == c->xs_own.p && (c->K == 0 || c->ys == c->ys_own.p), ISOKANN_ERR_STATE,
                "append needs library-owned data (isokann_set_data)");
     IK_REQUIRE(xs_new && D == c->D && n_new >= 0 && (c->K == 0 || (ys_new && K == c->K)), ISOKANN_BAD_ARGUMENT,
@@ -2000,6 +2037,7 @@ int32_t isokann_append_data(isokann_ctx *c, const float *xs_new, const float *ys
       c->ys_chunk_pts = 0;
       c->xs_pending = false;
     }
+    if (c->world > 1) gather_xs(*c);  // an asynchronous upload may have left other ranks' rows of xs to be fetched
     if (n_new == 0) return;
     const int64_t N0 = c->N, N1 = N0 + n_new;
     auto grow = [&](DevBuf<float> &buf, int64_t per_point) {
@@ -2015,15 +2053,21 @@ int32_t isokann_append_data(isokann_ctx *c, const float *xs_new, const float *ys
     IK_CUDA(cudaMemcpyAsync(c->xs_own.p + N0 * D, xs_new, (size_t)n_new * D * sizeof(float), cudaMemcpyHostToDevice,
                             c->stream));
     c->xs = c->xs_own.p;
-    if (c->K > 0) {
-      grow(c->ys_own, c->K * D);
-      IK_CUDA(cudaMemcpyAsync(c->ys_own.p + N0 * c->K * D, ys_new, (size_t)n_new * c->K * D * sizeof(float),
-                              cudaMemcpyHostToDevice, c->stream));
-      c->ys = c->ys_own.p;
+    if (c->world > 1) {
+      // every rank passes the same appended block; the contiguous split of N0 + n_new moves all shard boundaries
+      sync_stream(*c);
+      reshard_ys(*c, N0, 0, N1, ys_new);
+    } else {
+      if (c->K > 0) {
+        grow(c->ys_own, c->K * D);
+        IK_CUDA(cudaMemcpyAsync(c->ys_own.p + N0 * c->K * D, ys_new, (size_t)n_new * c->K * D * sizeof(float),
+                                cudaMemcpyHostToDevice, c->stream));
+        c->ys = c->ys_own.p;
+      }
+      sync_stream(*c);
+      c->N = N1;
+      c->n_loc = N1;
     }
-    sync_stream(*c);
-    c->N = N1;
-    c->n_loc = N1;
     c->has_target = false;
     c->has_weights = false;
   });
@@ -2031,7 +2075,6 @@ int32_t isokann_append_data(isokann_ctx *c, const float *xs_new, const float *ys
 
 int32_t isokann_keep_last(isokann_ctx *c, int64_t n_keep) {
   return guarded(c, [&] {
-    IK_REQUIRE(c->world == 1, ISOKANN_ERR_STATE, "isokann_keep_last is single-rank only");
     IK_REQUIRE(c->xs != nullptr && c->xs == c->xs_own.p && (c->K == 0 || c->ys == c->ys_own.p), ISOKANN_ERR_STATE,
                "keep_last needs library-owned data (isokann_set_data)");
     IK_REQUIRE(n_keep >= 1, ISOKANN_BAD_ARGUMENT, "n_keep must be positive");
@@ -2041,6 +2084,7 @@ int32_t isokann_keep_last(isokann_ctx *c, int64_t n_keep) {
       c->ys_chunk_pts = 0;
       c->xs_pending = false;
     }
+    if (c->world > 1) gather_xs(*c);
     const int64_t drop = c->N - n_keep;
     auto shift = [&](DevBuf<float> &buf, int64_t per_point) {
       DevBuf<float> nb;
@@ -2053,12 +2097,16 @@ int32_t isokann_keep_last(isokann_ctx *c, int64_t n_keep) {
     };
     shift(c->xs_own, c->D);
     c->xs = c->xs_own.p;
-    if (c->K > 0) {
-      shift(c->ys_own, c->K * c->D);
-      c->ys = c->ys_own.p;
+    if (c->world > 1) {
+      reshard_ys(*c, c->N, drop, n_keep, nullptr);
+    } else {
+      if (c->K > 0) {
+        shift(c->ys_own, c->K * c->D);
+        c->ys = c->ys_own.p;
+      }
+      c->N = n_keep;
+      c->n_loc = n_keep;
     }
-    c->N = n_keep;
-    c->n_loc = n_keep;
     c->has_target = false;
     c->has_weights = false;
   });

@@ -57,6 +57,19 @@ def exchange_slices(lo: int, hi: int, world: int):
     return out
 
 
+def reshard_plan(n_old: int, shift: int, n_new: int, world: int, rank: int):
+    """Incremental data on several ranks (isokann_append_data: shift = 0, n_new = n_old + appended;
+    isokann_keep_last: shift = dropped, n_new = kept): new start point i is old start point i + shift while that is
+    < n_old, else row i + shift - n_old of the appended block.  Returns for ``rank``
+    ((offset, length) of its new shard, (a, b) old global rows it keeps -> local rows [0, b - a),
+    (a2, b2) "old-global" rows it takes from the appended block -> appended rows [a2 - n_old, b2 - n_old)),
+    the rule of reshard_ys in csrc/api.cu."""
+    o1, l1 = shard_range(n_new, world, rank)
+    a, b = o1 + shift, min(o1 + l1 + shift, n_old)
+    a2, b2 = max(o1 + shift, n_old), o1 + l1 + shift
+    return (o1, l1), (a, max(a, b)), (a2, max(a2, b2))
+
+
 def broadcast_unique_id(rank: int, src: int = 0) -> Optional[bytes]:
     """rank ``src`` creates the NCCL unique id, torch.distributed broadcasts it to everyone"""
     import torch.distributed as dist

@@ -13,6 +13,53 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
+def incremental_data_check(pkg, world, rank, local):
+    """addcoords! and the cutoff window of run_kde! (src/iso.jl:238,288-290) on several ranks: isokann_append_data /
+    isokann_keep_last rebuild every rank's shard of ys on the device; afterwards the context must behave bit for bit
+    like a fresh multi-rank upload of the same data (same shards -> same kernels, same summation order)."""
+    failures = []
+    w = pkg.synthetic.WORKLOADS["c1"]
+    N0, n_new, K, keep = 501, 203, 3, 397             # odd sizes: every shard boundary moves
+    xs, ys = pkg.synthetic.make_data(w, N0 + n_new, K)
+    flat0 = pkg.densenet(w.widths, layernorm=True, rng=np.random.default_rng(11)).flat()
+
+    def make(lo, hi):
+        m = pkg.Chain(list(w.widths), True).load_flat(flat0)
+        data = pkg.SimulationData(xs[:, lo:hi], ys[:, :, lo:hi], featurizer=pkg.FeaturesAll())
+        return pkg.Iso(data, opt=pkg.AdamRegularized(), model=m, minibatch=100, device=local,
+                       comm=(world, rank, pkg.parallel.broadcast_unique_id(rank)))
+
+    inc = make(0, N0)
+    k0 = pkg.koopman(inc)                               # touch the data before it grows
+    pkg.addcoords_(inc, xs[:, N0:], ys[:, :, N0:])
+    fresh = make(0, N0 + n_new)
+    if not (len(inc.data) == N0 + n_new and np.array_equal(pkg.koopman(inc), pkg.koopman(fresh))
+            and np.array_equal(pkg.koopman(inc)[:, :N0], k0)):
+        failures.append(("append", "Koopman vector differs from a fresh upload"))
+    perms = pkg.synthetic.make_perms(w, N0 + n_new, 2)
+    pkg.run_(inc, 2, perms=perms)
+    pkg.run_(fresh, 2, perms=perms)
+    if not (np.array_equal(inc.losses, fresh.losses)
+            and np.array_equal(inc.engine.download_params(), fresh.engine.download_params())):
+        failures.append(("append", "training after the append differs", inc.losses, fresh.losses))
+    pkg.cutoff_(inc, keep)
+    last = make(N0 + n_new - keep, N0 + n_new)
+    last.engine.upload_params(inc.engine.download_params())
+    last.engine.upload_opt_state(*inc.engine.download_opt_state())
+    if not (len(inc.data) == keep and np.array_equal(pkg.koopman(inc), pkg.koopman(last))
+            and np.array_equal(pkg.chis(inc), pkg.chis(last))):
+        failures.append(("keep_last", "chi / Koopman vector differ from a fresh upload of the window"))
+    perms = pkg.synthetic.make_perms(w, keep, 2)
+    pkg.run_(inc, 2, perms=perms)
+    pkg.run_(last, 2, perms=perms)
+    if not (np.array_equal(inc.losses[-2:], last.losses[-2:])
+            and np.array_equal(inc.engine.download_params(), last.engine.download_params())):
+        failures.append(("keep_last", "training after the cutoff differs", inc.losses[-2:], last.losses[-2:]))
+    for iso_ in (inc, fresh, last):
+        iso_.engine.close()
+    return failures
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -23,7 +70,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import copy
     failures = []
-    for name, widths, target, N, K, B, gemm in [("c1", None, "shiftscale", 1003, 3, 250, "auto"),
+    # ISOKANN_MULTI_CASES="0,6" restricts the run to some of the cases below, "none" to the incremental-data part only
+    sel = os.environ.get("ISOKANN_MULTI_CASES", "")
+    cases = [("c1", None, "shiftscale", 1003, 3, 250, "auto"),
                                                 ("c4", [231, 38, 6, 3], "pinv", 777, 2, 128, "auto"),
                                                 ("c4", [231, 38, 6, 2], "isa", 640, 2, 0, "auto"),
                                                 ("c1", [231, 256, 256, 1], "shiftscale", 900, 2, 300, "tc"),
@@ -31,7 +80,10 @@ def main():
                                                 ("c1", [231, 512, 1], "shiftscale", 700, 2, 0, "tc"),
                                                 # triple well: identity featurizer, no LayerNorm, F = 2 (the fused
                                                 # narrow step once read uninitialised shared memory here)
-                                                ("c2", None, "shiftscale", 1000, 3, 250, "auto")]:
+                                                ("c2", None, "shiftscale", 1000, 3, 250, "auto")]
+    if sel:
+        cases = [] if sel == "none" else [cases[int(i)] for i in sel.split(",")]
+    for name, widths, target, N, K, B, gemm in cases:
         w = copy.deepcopy(pkg.synthetic.WORKLOADS[name])
         if widths:
             w.widths = widths
@@ -114,6 +166,7 @@ def main():
         dist.broadcast(ref, 0)
         if not torch.equal(t, ref):
             failures.append((name, "replicas diverged"))
+    failures += incremental_data_check(pkg, world, rank, local)
     flag = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(flag)
     if rank == 0:

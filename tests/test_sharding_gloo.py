@@ -81,3 +81,60 @@ def test_world2_matches_single_process(tmp_path, pkg, oracle):
     loss = oracle.train_batch(m, xsf, target, cfg, oracle.opt_init(cfg, oracle.num_params(m)), B, perm)
     assert np.isclose(loss, float(r0["loss"]), rtol=1e-6)
     assert np.abs(oracle.flatten_params(m) - r0["flat"]).max() < 2e-5
+
+
+def _reshard_worker(rank, world, port, out_dir):
+    """the data movement of isokann_append_data / isokann_keep_last with several ranks (reshard_ys, csrc/api.cu):
+    all-gather the padded old shards, cut the new range out of the gathered copy, take the rest from the appended
+    block -- with gloo tensors standing in for device buffers"""
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    par = g.load_package().parallel
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal((1000, 6)).astype(np.float32)     # global rows; every rank can index the "host" copy
+    ok = True
+    for n_old, appended, keep in [(501, 203, 397), (7, 1, 3), (64, 64, 1), (5, 0, 5), (3, 8, 2)]:
+        off, n = par.shard_range(n_old, world, rank)
+        local = data[off:off + n]
+        for shift, n_new, block in [(0, n_old + appended, data[n_old:n_old + appended]), (n_old - keep, keep, None)]:
+            nmax = -(-n_old // world)
+            pad = np.zeros((nmax, 6), np.float32)
+            pad[:n] = local
+            bufs = [torch.zeros(nmax, 6) for _ in range(world)]
+            dist.all_gather(bufs, torch.from_numpy(pad))
+            full = np.concatenate([bufs[r].numpy()[:par.shard_range(n_old, world, r)[1]] for r in range(world)])
+            (o1, l1), (a, b), (a2, b2) = par.reshard_plan(n_old, shift, n_new, world, rank)
+            new = np.full((l1, 6), np.nan, np.float32)
+            new[:b - a] = full[a:b]
+            if b2 > a2:
+                new[a2 - shift - o1:b2 - shift - o1] = block[a2 - n_old:b2 - n_old]
+            expect = (data[:n_new] if shift == 0 else data[shift:shift + n_new])[o1:o1 + l1]
+            ok = ok and np.array_equal(new, expect)
+    Path(out_dir, f"reshard{rank}.txt").write_text("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_world2_reshard_plan(tmp_path, pkg):
+    import torch.multiprocessing as mp
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_reshard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "reshard0.txt").read_text() == "ok" and (tmp_path / "reshard1.txt").read_text() == "ok"
+    # the same rule for other world sizes, without processes
+    par = pkg.parallel
+    for world in (3, 8):
+        for n_old, shift, n_new in [(501, 0, 704), (704, 307, 397), (5, 0, 6), (9, 8, 1)]:
+            rows = []
+            for r in range(world):
+                (o1, l1), (a, b), (a2, b2) = par.reshard_plan(n_old, shift, n_new, world, r)
+                got = list(range(a, b)) + list(range(a2, b2))
+                assert got == list(range(o1 + shift, o1 + shift + l1))
+                rows += got
+            assert rows == list(range(shift, shift + n_new))
