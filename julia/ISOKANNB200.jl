@@ -77,6 +77,7 @@ end
 Base.getproperty(m::B200Model, s::Symbol) = s === :layers ? getfield(m, :chain).layers : getfield(m, s)
 ISOKANN.inputdim(m::B200Model) = ISOKANN.inputdim(m.chain)
 ISOKANN.outputdim(m::B200Model) = ISOKANN.outputdim(m.chain)
+ISOKANN.iscuda(::B200Model) = false     # callers hand over and receive host arrays (src/iso.jl:211, src/models.jl:35)
 
 function check(m::B200Model, rc::Int32)
     rc == 0 && return
