@@ -123,9 +123,11 @@ int32_t isokann_abi_version(void);
 
 /* Iso(data; model, opt) -> handle (src/iso.jl:17-43).  Parameters are zero until uploaded. */
 int32_t isokann_create(const isokann_config *cfg, isokann_ctx **out);
-int32_t isokann_destroy(isokann_ctx *ctx);
-const char *isokann_last_error(const isokann_ctx *ctx);
+int32_t isokann_destroy(isokann_ctx *ctx);                /* the Julia finalizer of the model wrapper */
+const char *isokann_last_error(const isokann_ctx *ctx);   /* message of the DomainError / error to throw */
 
+/* length of the flat parameter vector (sum(length, Flux.trainables(model))); inputdim(model) (src/models.jl:26-27)
+ * as implied by the featurizer; size(coords, 1) the featurizer expects */
 int64_t isokann_num_params(const isokann_ctx *ctx);
 int32_t isokann_feature_dim(const isokann_ctx *ctx);  /* F implied by the featurizer          */
 int32_t isokann_coord_dim(const isokann_ctx *ctx);    /* D expected in coordinate records      */
@@ -197,14 +199,15 @@ int32_t isokann_forward(isokann_ctx *ctx, const float *in, int64_t rows, int64_t
  * metadynamics bias (src/simulators/metadynamics.jl:40-49) and optimal control differentiate through. */
 int32_t isokann_chi_vjp(isokann_ctx *ctx, const float *in, int64_t rows, int64_t M, int32_t is_features,
                         const float *cot, float *grad_out);
-/* chis(iso) on the resident xs -> d x N */
+/* chis(iso) = model(features(data)) (src/iso.jl:203) on the resident xs -> d x N */
 int32_t isokann_chis(isokann_ctx *ctx, float *chi_out);
 /* expectation(model, propfeatures(data)) (src/isotarget.jl:18,20) on the resident ys -> d x N */
 int32_t isokann_koopman(isokann_ctx *ctx, float *kchi_out);
 /* isotarget(target, model, xs, ys) (src/isotarget.jl:12,34,100-107,152-179); the target stays
  * resident for train_epoch; target_out (d x N) may be NULL */
 int32_t isokann_target(isokann_ctx *ctx, int32_t transform, const isokann_target_opts *opts, float *target_out);
-/* the resident target (d x N) of the last isokann_target / isokann_set_target, for loggers that look at it */
+/* the resident target (d x N) of the last isokann_target / isokann_set_target, for loggers that look at it
+ * (log!(logger; iso) in run!, src/iso.jl:85-89) */
 int32_t isokann_download_target(isokann_ctx *ctx, float *target_out);
 /* validationloss(iso, valdata) (src/iso.jl:160-168): mean((chi(vx) - shiftscale([K chi(vy); K chi(ys)])[1:Nv])^2)
  * in one call; vxs is D x Nv, vys is D x K x Nv (host, column-major).  Only the scalar leaves the device.
@@ -239,7 +242,9 @@ int32_t isokann_residual_ritz(isokann_ctx *ctx, double *vals_out, double *vecs_o
  * src/iso.jl:181): Xoshiro256++ state in/out (s0..s3 of the Xoshiro struct / task-local RNG), 1-based permutation
  * out.  Host-side (the algorithm is inherently sequential).  UNPINNED against a real Julia session. */
 int32_t isokann_randperm(uint64_t *state4, int64_t n, int64_t *perm_out);
-/* user-defined isotarget methods: upload a d x N target computed on the host */
+/* user-defined isotarget methods (any isotarget(iso, target) dispatched at src/isotarget.jl:10-12, e.g.
+ * scripts/251126_carsten/main.jl:132, and the experimental transforms of src/isotarget.jl:190-824): upload a d x N
+ * target computed on the host */
 int32_t isokann_set_target(isokann_ctx *ctx, const float *target, int64_t d, int64_t N);
 /* train_batch!(model, xs, target, opt, minibatch; shuffle, partial) (src/iso.jl:179-194).  perm
  * is the 1-based randperm(N) the DataLoader would draw; returns sum(l)/N in *loss_out */
