@@ -48,7 +48,29 @@ def case(pkg, name, widths, N, K, B, n_iter, opt, target, seed_model, topts=None
                 name=name, opt=opt, target=target, topts=np.array(sorted(k for k, v in topts.items() if v is False)))
 
 
+def diagnostics_fixture():
+    """chi / Kchi of the final models of two committed cases and the oracle's rates / residual_subspace /
+    residual_ritz on them.  Written to diagnostics.npz only; the other fixtures are not touched."""
+    out = {}
+    for key in ("adp_shiftscale_adam", "adp_isa_2d"):
+        z = np.load(OUT / f"{key}.npz")
+        widths = [int(v) for v in z["widths"]]
+        rec = lambda a: np.ascontiguousarray(np.asarray(a).T)
+        xsf, ysf = oracle.flatpairdists(rec(z["xs"])), oracle.flatpairdists(rec(z["ys"]))
+        m = oracle.unflatten_params(oracle.Model(widths, True), z["flat_final"])
+        chi, kchi = oracle.forward(m, xsf), oracle.expectation(m, ysf)
+        res, relres = oracle.residual_subspace(chi, kchi)
+        _, ritz_relres, vals, _, _ = oracle.residual_ritz(chi, kchi)
+        out.update({f"{key}__chi": chi, f"{key}__kchi": kchi, f"{key}__rates": np.real(oracle.rates(chi, kchi)),
+                    f"{key}__res": res, f"{key}__relres": relres, f"{key}__ritz_relres": ritz_relres,
+                    f"{key}__ritz_vals": np.asarray(vals, dtype=np.complex128)})
+    np.savez_compressed(OUT / "diagnostics.npz", **out)
+    print("wrote diagnostics")
+
+
 def main():
+    if "--diagnostics-only" in sys.argv:
+        return diagnostics_fixture()
     pkg = g.load_package()
     cases = {
         "adp_shiftscale_nesterov": ("c1", [231, 38, 6, 1], 48, 3, 16, 3, "nesterov", "shiftscale", 11),
@@ -67,6 +89,7 @@ def main():
     x = pkg.synthetic.ADP_NM
     d = np.array([np.linalg.norm(x[i] - x[j]) for j in range(1, 22) for i in range(j)])
     np.savez_compressed(OUT / "adp_geometry.npz", coords_nm=x, pairdists=d)
+    diagnostics_fixture()
 
 
 if __name__ == "__main__":
