@@ -217,8 +217,9 @@ int32_t isokann_validationloss(isokann_ctx *ctx, const float *vxs, const float *
 /* Diagnostics on the resident data (loggers call them every `logevery` iterations; in the reference each of them pulls
  * chi and Kchi to the host).  chi = chis(iso), Kchi = koopman(iso) are evaluated on the device, their second moments
  * and the residual column norms are fp64 device reductions, the d x d algebra runs on the host in double precision
- * (the reference: Float32 `/` and `log` for rates, Float64 for the residuals).  With several ranks every rank returns
- * the same result.  Matrices are column-major as in Julia.
+ * (the reference: Float32 `/` and `log` for rates, Float64 for the residuals).  With several ranks the calls are
+ * collective (chi and Kchi are all-gathered: every rank must make the call) and every rank returns the same result.
+ * Matrices are column-major as in Julia.
  *
  * rates(iso) (src/iso.jl:339-351) WITHOUT the division by lagtime(sim): Q = log(Kchi / chi), `/` the least-squares
  * right division.  One dimensional chi: rows [chi; 1 - chi] and [Kchi; 1 - Kchi] (:346-349), Q is 2 x 2.
